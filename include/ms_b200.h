@@ -1,0 +1,129 @@
+/*
+ * ms_b200.h - C ABI of the B200-native Vicon Nexus loader / windowing / NMF-MU library
+ * (libms_b200.so, built from muscle_synergies_b200/csrc/ for sm_100a).
+ *
+ * The reference (elvis-sik/muscle_synergies) is pure Python and has no FFI; the seam this
+ * library replaces is the body of
+ *     load_vicon_file(csv_filename)            src/muscle_synergies/vicon_data/load_csv.py:96-135
+ * below the 2 x 5 header lines, i.e. for every data row
+ *     csv.reader tokenisation                  load_csv.py:21-31
+ *     GettingMeasurementsState._is_blank_line  reader.py:886-901
+ *     DataState._parse_row / float()           reader.py:927-948
+ *     DeviceAggregator.add_data column cut     aggregator.py:96-124, 229-241
+ *     Builder._extract_dataframe               user_data.py:391-396   (float64, channel-major block)
+ * and, for the windowing of project/segment.py,
+ *     _transition_indices                      segment.py:667-755
+ *     DeviceData.__getitem__(slice) row cuts   user_data.py:727-731
+ * plus the declared extension behind find_synergies / vaf (analysis.py:597-667, 713-914).
+ *
+ * Conventions
+ *   - plain C types only; every pointer named d_* is DEVICE memory owned by the caller,
+ *     h_* is host memory; the library allocates nothing persistent.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - every entry point returns 0 on success or a negative MS_E_* code; kernels are
+ *     enqueued asynchronously on `stream` unless stated otherwise.
+ *   - re-entrant: no global mutable state; one workspace per concurrent call.
+ */
+#ifndef MS_B200_H
+#define MS_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MS_OK 0
+#define MS_E_INVALID (-1)   /* bad argument (null pointer, misaligned buffer, bad size) */
+#define MS_E_CUDA (-2)      /* a CUDA runtime call failed; see ms_last_cuda_error() */
+#define MS_E_WORKSPACE (-3) /* workspace too small */
+#define MS_E_NO_DEVICE (-4) /* no CUDA device / wrong architecture */
+
+#define MS_TILE_BYTES 65536     /* bytes of CSV owned by one thread block */
+#define MS_MAX_ROW_BYTES 8192   /* longest supported CSV row (overhang read past a tile) */
+#define MS_MAX_BLANK_ROWS 8     /* blank rows reported by ms_scan (first ones, file order) */
+#define MS_MAX_SECTIONS 4
+
+/* flags in ms_scan_summary.flags */
+#define MS_SCAN_HAS_HIGH_BYTES 1u    /* some byte >= 0x80 */
+#define MS_SCAN_BLANK_OVERFLOW 2u    /* more blank rows than can be ordered exactly */
+#define MS_SCAN_HAS_CR 4u
+
+/* Result of ms_scan: written to DEVICE memory (copy it back after the stream is done). */
+typedef struct ms_scan_summary {
+    int64_t n_bytes;
+    int64_t n_rows;        /* csv rows: terminators (\n, \r\n, lone \r) + unterminated last row */
+    int64_t n_terminators;
+    int64_t n_quotes;      /* '"' bytes in the whole buffer */
+    int64_t n_blank_rows;  /* rows whose every field is empty after str.strip() (reader.py:886-901) */
+    uint32_t flags;
+    uint32_t n_reported;   /* entries valid in the arrays below (<= MS_MAX_BLANK_ROWS) */
+    int64_t blank_row[MS_MAX_BLANK_ROWS];  /* 0-based csv row index of each blank row */
+    int64_t blank_end[MS_MAX_BLANK_ROWS];  /* byte offset of the last byte of its terminator
+                                              (== n_bytes for an unterminated last row) */
+} ms_scan_summary;
+
+/* One run of data rows that share a column layout (one per CSV section). */
+typedef struct ms_section {
+    int64_t row_begin;  /* first data row (0-based csv row index) */
+    int64_t row_end;    /* one past the last data row */
+    int32_t num_cols;   /* fields parsed per row: reader.py:241-243 (rest of the row is ignored) */
+    int32_t n_keep;     /* channels stored: csv columns [2, 2 + n_keep) (aggregator.py:96-124) */
+    double* d_out;      /* [n_keep][stride] float64, channel-major (user_data.py:396 block layout) */
+    int64_t stride;     /* elements between channels, >= row_end - row_begin */
+} ms_section;
+
+/* status key written by ms_parse: ~0 when every field parsed, else
+ * (byte offset of the first offending field << 3) | kind, minimum over the file. */
+#define MS_ERR_NONE 0xFFFFFFFFFFFFFFFFull
+#define MS_ERR_KIND_BAD_FLOAT 1u   /* float(field) raises ValueError */
+#define MS_ERR_KIND_NON_ASCII 2u   /* byte >= 0x80 in a numeric field: unsupported on device */
+#define MS_ERR_KIND_ROW_TOO_LONG 3u /* a row exceeds MS_MAX_ROW_BYTES */
+
+/* ---- loader ------------------------------------------------------------------------- */
+
+/* Bytes of device workspace needed to scan + parse a buffer of n_bytes. */
+int64_t ms_workspace_bytes(int64_t n_bytes);
+
+/* Pass 1: row terminators per tile, blank rows, quote count.  d_bytes must be 16-byte
+ * aligned and readable up to n_bytes rounded up to 16 (pad the allocation). */
+int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+            ms_scan_summary* d_summary, void* stream);
+
+/* Pass 2: parse the data rows of up to MS_MAX_SECTIONS sections into channel-major
+ * float64 arrays.  Needs the workspace filled by ms_scan for the same buffer.
+ * d_status: one uint64 in device memory (see MS_ERR_*). */
+int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
+             int32_t n_sections, uint64_t* d_status, void* stream);
+
+/* ---- windowing ------------------------------------------------------------------------ */
+
+/* _transition_indices (segment.py:667-755): alternating search for the first run of
+ * >= min_phase_size samples with exactly one / exactly two loaded plates (value != 0, NaN
+ * counts as loaded; a run cut short by the end of the signal counts).  Writes up to
+ * num_segments sample indices to d_transitions, for each of them which plates are loaded
+ * there to d_loaded (bit 0 left, bit 1 right; may be NULL) and the number found to
+ * d_n_found.  d_work: ms_transitions_workspace_bytes(n) bytes of device scratch. */
+int64_t ms_transitions_workspace_bytes(int64_t n);
+int ms_find_transitions(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
+                        int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded,
+                        int32_t* d_n_found, void* stream);
+
+/* DeviceData.__getitem__(slice) (user_data.py:727-731) for many windows at once: copies rows
+ * [start_w, stop_w) of every channel of a channel-major array (d_src[c * src_stride + row])
+ * to d_out[out_offset_w + c * (stop_w - start_w) + r].  max_window_len: the longest window
+ * (sizes the grid). */
+int ms_cut_windows(const double* d_src, int64_t src_stride, int32_t n_channels, const int64_t* d_starts,
+                   const int64_t* d_stops, const int64_t* d_out_offsets, int32_t n_windows, double* d_out,
+                   int64_t max_window_len, void* stream);
+
+/* ---- misc ------------------------------------------------------------------------------- */
+const char* ms_last_cuda_error(void);
+const char* ms_version(void);
+/* Number of kernels this library has launched in this process (bench.py gpu_launches). */
+int64_t ms_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MS_B200_H */

@@ -1,0 +1,30 @@
+"""muscle_synergies_b200: the Vicon Nexus CSV loader and trial windowing of
+elvis-sik/muscle_synergies, rebuilt for NVIDIA B200 (sm_100a).
+
+    import muscle_synergies_b200 as muscle_synergies
+    data = muscle_synergies.load_vicon_file("trial.csv")     # same call as the reference
+    data.emg.df            # pandas DataFrame, bit-identical to the reference loader's
+    data.emg.tensor        # (channels, rows) float64 CUDA tensor, zero-copy
+
+The data path is hand-written CUDA behind a C ABI (include/ms_b200.h, libms_b200.so);
+there is no CPU fallback.
+"""
+__version__ = "0.1.0"
+
+from .vicon_data import (  # noqa: F401
+    DeviceData,
+    DeviceType,
+    ViconLoader,
+    ViconNexusData,
+    load_vicon_bytes,
+    load_vicon_file,
+)
+
+__all__ = (
+    "load_vicon_file",
+    "load_vicon_bytes",
+    "ViconLoader",
+    "ViconNexusData",
+    "DeviceData",
+    "DeviceType",
+)

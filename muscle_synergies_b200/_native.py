@@ -1,0 +1,103 @@
+"""ctypes binding of libms_b200.so (the C ABI declared in include/ms_b200.h).
+
+There is no CPU fallback: if the shared library is missing or cannot be loaded this module
+raises, and so does everything that needs it.
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libms_b200.so")
+
+MS_TILE_BYTES = 65536
+MS_MAX_ROW_BYTES = 8192
+MS_MAX_BLANK_ROWS = 8
+MS_MAX_SECTIONS = 4
+
+MS_SCAN_HAS_HIGH_BYTES = 1
+MS_SCAN_BLANK_OVERFLOW = 2
+MS_SCAN_HAS_CR = 4
+
+MS_ERR_NONE = 0xFFFFFFFFFFFFFFFF
+MS_ERR_KIND_BAD_FLOAT = 1
+MS_ERR_KIND_NON_ASCII = 2
+MS_ERR_KIND_ROW_TOO_LONG = 3
+
+
+class ScanSummary(ctypes.Structure):
+    _fields_ = [
+        ("n_bytes", ctypes.c_int64),
+        ("n_rows", ctypes.c_int64),
+        ("n_terminators", ctypes.c_int64),
+        ("n_quotes", ctypes.c_int64),
+        ("n_blank_rows", ctypes.c_int64),
+        ("flags", ctypes.c_uint32),
+        ("n_reported", ctypes.c_uint32),
+        ("blank_row", ctypes.c_int64 * MS_MAX_BLANK_ROWS),
+        ("blank_end", ctypes.c_int64 * MS_MAX_BLANK_ROWS),
+    ]
+
+
+class Section(ctypes.Structure):
+    _fields_ = [
+        ("row_begin", ctypes.c_int64),
+        ("row_end", ctypes.c_int64),
+        ("num_cols", ctypes.c_int32),
+        ("n_keep", ctypes.c_int32),
+        ("d_out", ctypes.c_void_p),
+        ("stride", ctypes.c_int64),
+    ]
+
+
+class NativeError(RuntimeError):
+    pass
+
+
+_lib = None
+
+
+def _declare(L):
+    vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
+    sigs = {
+        "ms_workspace_bytes": (i64, [i64]),
+        "ms_scan": (ctypes.c_int, [vp, i64, vp, i64, vp, vp]),
+        "ms_parse": (ctypes.c_int, [vp, i64, vp, ctypes.POINTER(Section), i32, vp, vp]),
+        "ms_transitions_workspace_bytes": (i64, [i64]),
+        "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),
+        "ms_cut_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp]),
+        "ms_last_cuda_error": (ctypes.c_char_p, []),
+        "ms_version": (ctypes.c_char_p, []),
+        "ms_launch_count": (i64, []),
+    }
+    for name, (res, args) in sigs.items():
+        fn = getattr(L, name)  # AttributeError here = the library does not export what the header declares
+        fn.restype = res
+        fn.argtypes = args
+    return sigs
+
+
+def lib():
+    """Returns the loaded library; raises NativeError when it is not built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise NativeError(
+            f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+            "(nvcc, sm_100a). muscle_synergies_b200 has no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    _declare(L)
+    _lib = L
+    return L
+
+
+def check(code: int, what: str):
+    if code != 0:
+        names = {-1: "MS_E_INVALID", -2: "MS_E_CUDA", -3: "MS_E_WORKSPACE", -4: "MS_E_NO_DEVICE"}
+        detail = lib().ms_last_cuda_error().decode() if code == -2 else ""
+        raise NativeError(f"{what} failed: {names.get(code, code)} {detail}".strip())
+
+
+def launch_count() -> int:
+    return int(lib().ms_launch_count())

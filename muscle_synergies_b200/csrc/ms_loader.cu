@@ -1,0 +1,767 @@
+// Vicon Nexus CSV loader kernels for sm_100a.
+//
+//   ms_scan_kernel     pass 1, one CTA per 64 KiB tile: row terminators, quotes, blank rows
+//   ms_resolve_kernel  single CTA: terminator prefix per tile, blank rows that straddle
+//                      tiles, their csv row indices -> ms_scan_summary
+//   ms_parse_kernel    pass 2, one CTA per tile: (row, column) of every field by a block-wide
+//                      segmented scan over delimiter masks, correctly rounded decimal->double
+//                      per field, scatter into channel-major float64 arrays
+//
+// Replaces the per-row Python of the reference (reader.py:886-948, aggregator.py:96-124,
+// 229-241, user_data.py:391-396); see include/ms_b200.h for the boundary.
+#include <stdio.h>
+
+#include "ms_common.cuh"
+#include "ms_parse_double.cuh"
+
+// ---- workspace layout ------------------------------------------------------------------------
+struct MsTileInfo {
+    uint32_t n_term;      // terminator ends inside the tile
+    uint32_t flags;       // MS_TI_*
+    int32_t first_term;   // tile-relative offset of the first terminator end, -1 if none
+    int32_t last_term;    // tile-relative offset of the last terminator end, -1 if none
+    uint32_t n_quotes;
+    uint32_t n_blank;     // blank rows fully decided inside the tile
+    int32_t blank_pos[2]; // tile-relative terminator-end offsets of the first two of them
+};
+#define MS_TI_HAS_TERM 1u
+#define MS_TI_NB_TAIL 2u    // non-blank byte after the last terminator (or anywhere if none)
+#define MS_TI_NB_HEAD 4u    // non-blank byte before the first terminator
+#define MS_TI_HIGH 8u       // byte >= 0x80 present
+#define MS_TI_OVERFLOW 16u  // more than MS_TILE_BLANK_CAP blank rows in the tile
+#define MS_TI_HAS_CR 32u
+
+#define MS_TILE_BLANK_CAP 16
+
+static inline int64_t ms_num_tiles(int64_t n) { return (n + MS_TILE_BYTES - 1) / MS_TILE_BYTES; }
+
+struct MsWorkspaceView {
+    MsTileInfo* tiles;
+    unsigned long long* term_prefix;  // terminator ends before the tile
+};
+
+__host__ __device__ static inline int64_t ms_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
+
+static MsWorkspaceView ms_view(void* ws, int64_t n_tiles) {
+    MsWorkspaceView v;
+    v.tiles = (MsTileInfo*)ws;
+    v.term_prefix = (unsigned long long*)((char*)ws + ms_align_up(n_tiles * (int64_t)sizeof(MsTileInfo), 256));
+    return v;
+}
+
+extern "C" int64_t ms_workspace_bytes(int64_t n_bytes) {
+    int64_t t = ms_num_tiles(n_bytes < 1 ? 1 : n_bytes);
+    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256);
+}
+
+// ---- shared helpers --------------------------------------------------------------------------------
+// 16-byte load with everything at or beyond n replaced by `fill`.
+__device__ __forceinline__ uint4 ms_load16(const uint8_t* __restrict__ src, int64_t off, int64_t n, uint32_t fill_rep) {
+    if (off + 16 <= n) return __ldg(reinterpret_cast<const uint4*>(src + off));
+    uint32_t w[4] = {fill_rep, fill_rep, fill_rep, fill_rep};
+    if (off < n) {
+        // the allocation is readable up to n rounded up to 16 (ABI requirement)
+        uint4 v = __ldg(reinterpret_cast<const uint4*>(src + off));
+        uint32_t r[4] = {v.x, v.y, v.z, v.w};
+        int valid = (int)(n - off);
+        for (int i = 0; i < 4; i++) {
+            int k = valid - 4 * i;
+            if (k >= 4)
+                w[i] = r[i];
+            else if (k > 0) {
+                uint32_t m = (1u << (8 * k)) - 1u;
+                w[i] = (r[i] & m) | (fill_rep & ~m);
+            }
+        }
+    }
+    return make_uint4(w[0], w[1], w[2], w[3]);
+}
+
+// ===================================================================================================
+// pass 1
+// ===================================================================================================
+#define SCAN_THREADS 256
+#define SCAN_WARPS (SCAN_THREADS / 32)
+
+struct MsRun {  // state of the row in progress
+    uint32_t has_term;  // a terminator was seen (in the span this state summarises)
+    uint32_t nb_tail;   // non-blank byte since the last terminator (or since the span start)
+};
+__device__ __forceinline__ MsRun ms_run_combine(MsRun a, MsRun b) {
+    MsRun r;
+    r.has_term = a.has_term | b.has_term;
+    r.nb_tail = b.has_term ? b.nb_tail : (a.nb_tail | b.nb_tail);
+    return r;
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __restrict__ src, int64_t n,
+                                                                MsTileInfo* __restrict__ tiles) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t t0 = tile * (int64_t)MS_TILE_BYTES;
+
+    __shared__ MsRun s_warp_run[2][SCAN_WARPS];
+    __shared__ int s_blank_count;
+    __shared__ int s_blank[MS_TILE_BLANK_CAP];
+    __shared__ int s_first_term, s_last_term;
+    __shared__ uint32_t s_nb_head;
+    __shared__ uint32_t s_nterm, s_nquote, s_flags;
+
+    if (tid == 0) {
+        s_blank_count = 0;
+        s_first_term = -1;
+        s_last_term = -1;
+        s_nb_head = 0;
+        s_nterm = 0;
+        s_nquote = 0;
+        s_flags = 0;
+    }
+    __syncthreads();
+
+    MsRun run;  // block-uniform: state at the start of the current iteration
+    run.has_term = 0;
+    run.nb_tail = 0;
+    uint32_t my_nterm = 0, my_nquote = 0, my_flags = 0;
+
+    const int iters = MS_TILE_BYTES / (SCAN_THREADS * 16);
+    for (int it = 0; it < iters; it++) {
+        const int rel = (it * SCAN_THREADS + tid) * 16;
+        const int64_t off = t0 + rel;
+        // beyond the end: commas (blank, not a terminator)
+        uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
+        MsDelims d = ms_delims16(v);
+        uint32_t quote = ms_mask16(ms_eq_flags(v.x, 0x22222222u), ms_eq_flags(v.y, 0x22222222u),
+                                   ms_eq_flags(v.z, 0x22222222u), ms_eq_flags(v.w, 0x22222222u));
+        uint32_t ws = ms_mask16(ms_strip_space_flags(v.x), ms_strip_space_flags(v.y), ms_strip_space_flags(v.z),
+                                ms_strip_space_flags(v.w));
+        uint32_t nb = ~(ws | d.comma) & 0xffffu;
+        if ((v.x | v.y | v.z | v.w) & 0x80808080u) my_flags |= MS_TI_HIGH;
+        if (d.cr) my_flags |= MS_TI_HAS_CR;
+        // byte after this vector: first byte of the next lane's vector
+        uint32_t next_lf = __shfl_down_sync(0xffffffffu, d.lf & 1u, 1);
+        if (lane == 31) next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
+        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
+        my_nterm += __popc(term);
+        my_nquote += __popc(quote);
+
+        const uint32_t has_t = term != 0;
+        uint32_t nb_head, nb_tail;
+        if (has_t) {
+            uint32_t low = term & (0u - term);
+            nb_head = (nb & (low - 1u)) != 0;
+            int hi = 31 - __clz(term);
+            nb_tail = (nb >> (hi + 1)) != 0;
+        } else {
+            nb_head = nb_tail = nb != 0;
+        }
+
+        // ---- warp level: which non-blank state precedes each lane
+        const uint32_t HT = __ballot_sync(0xffffffffu, has_t);
+        const uint32_t NT = __ballot_sync(0xffffffffu, nb_tail);
+        const uint32_t below = (1u << lane) - 1u;
+        // warp aggregate
+        if (lane == 0) {
+            MsRun w;
+            if (HT) {
+                int last = 31 - __clz(HT);
+                w.has_term = 1;
+                w.nb_tail = (NT >> last) != 0;  // tail of lane `last` and every lane after it
+            } else {
+                w.has_term = 0;
+                w.nb_tail = NT != 0;
+            }
+            s_warp_run[it & 1][warp] = w;
+        }
+        __syncthreads();
+        // state before this warp = run (previous iterations) + warps before it
+        MsRun before = run;
+        for (int w = 0; w < warp; w++) before = ms_run_combine(before, s_warp_run[it & 1][w]);
+        MsRun after = before;
+        for (int w = warp; w < SCAN_WARPS; w++) after = ms_run_combine(after, s_warp_run[it & 1][w]);
+
+        if (has_t) {
+            // state just before this lane's vector
+            uint32_t ht = HT & below;
+            uint32_t carry, known;
+            if (ht) {
+                int j = 31 - __clz(ht);
+                carry = ((NT & below) >> j) != 0;
+                known = 1;
+            } else {
+                carry = before.nb_tail | ((NT & below) != 0);
+                known = before.has_term;
+            }
+            const int first_bit = __ffs(term) - 1;
+            const int pos = rel + first_bit;
+            if (known) {
+                if (!(carry | nb_head)) {  // the row ending at my first terminator is blank
+                    int slot = atomicAdd(&s_blank_count, 1);
+                    if (slot < MS_TILE_BLANK_CAP) s_blank[slot] = pos;
+                }
+            } else {
+                // first terminator of the tile: its row began in an earlier tile
+                s_first_term = pos;
+                s_nb_head = carry | nb_head;
+            }
+            // rows that begin and end inside this vector
+            uint32_t rest = term & (term - 1u);
+            int prev = first_bit;
+            while (rest) {
+                int b = __ffs(rest) - 1;
+                rest &= rest - 1u;
+                uint32_t between = (nb >> (prev + 1)) & ((1u << (b - prev - 1)) - 1u);
+                if (!between) {
+                    int slot = atomicAdd(&s_blank_count, 1);
+                    if (slot < MS_TILE_BLANK_CAP) s_blank[slot] = rel + b;
+                }
+                prev = b;
+            }
+            atomicMax(&s_last_term, rel + (31 - __clz(term)));
+        }
+        run = after;
+        // s_warp_run[it & 1] is rewritten two iterations later, after another barrier
+    }
+
+    // ---- tile totals
+    for (int o = 16; o > 0; o >>= 1) {
+        my_nterm += __shfl_down_sync(0xffffffffu, my_nterm, o);
+        my_nquote += __shfl_down_sync(0xffffffffu, my_nquote, o);
+        my_flags |= __shfl_down_sync(0xffffffffu, my_flags, o);
+    }
+    if (lane == 0) {
+        atomicAdd(&s_nterm, my_nterm);
+        atomicAdd(&s_nquote, my_nquote);
+        atomicOr(&s_flags, my_flags);
+    }
+    __syncthreads();
+    if (tid == 0) {
+        MsTileInfo ti;
+        ti.n_term = s_nterm;
+        ti.n_quotes = s_nquote;
+        ti.first_term = s_first_term;
+        ti.last_term = s_last_term;
+        uint32_t f = s_flags;
+        if (run.has_term) f |= MS_TI_HAS_TERM;
+        if (run.nb_tail) f |= MS_TI_NB_TAIL;
+        if (s_nb_head) f |= MS_TI_NB_HEAD;
+        int nbk = s_blank_count;
+        if (nbk > MS_TILE_BLANK_CAP) {
+            f |= MS_TI_OVERFLOW;
+            nbk = MS_TILE_BLANK_CAP;
+        }
+        // two smallest positions, ascending
+        int a = 0x7fffffff, b = 0x7fffffff;
+        for (int i = 0; i < nbk; i++) {
+            int p = s_blank[i];
+            if (p < a) {
+                b = a;
+                a = p;
+            } else if (p < b) {
+                b = p;
+            }
+        }
+        ti.n_blank = (uint32_t)s_blank_count;
+        ti.blank_pos[0] = a == 0x7fffffff ? -1 : a;
+        ti.blank_pos[1] = b == 0x7fffffff ? -1 : b;
+        ti.flags = f;
+        tiles[tile] = ti;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------
+// resolve: single CTA
+// ---------------------------------------------------------------------------------------------------
+#define RESOLVE_THREADS 1024
+#define RESOLVE_CAND_CAP 64
+
+// terminator ends in [from, to) of the buffer (cooperative, whole block); result valid in thread 0
+__device__ unsigned long long ms_block_count_terms(const uint8_t* __restrict__ src, int64_t n, int64_t from, int64_t to,
+                                                   unsigned long long* s_acc) {
+    if (threadIdx.x == 0) *s_acc = 0;
+    __syncthreads();
+    unsigned long long mine = 0;
+    const int64_t first_vec = from / 16, last_vec = (to + 15) / 16;
+    for (int64_t vi = first_vec + threadIdx.x; vi < last_vec; vi += blockDim.x) {
+        int64_t off = vi * 16;
+        uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
+        MsDelims d = ms_delims16(v);
+        uint32_t next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
+        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
+        // keep bytes in [from, to)
+        if (off < from) term &= ~((1u << (from - off)) - 1u);
+        if (off + 16 > to) term &= (1u << (to - off)) - 1u;
+        mine += __popc(term);
+    }
+    if (mine) atomicAdd(s_acc, mine);
+    __syncthreads();
+    return *s_acc;
+}
+
+__global__ void __launch_bounds__(RESOLVE_THREADS)
+    ms_resolve_kernel(const uint8_t* __restrict__ src, int64_t n, const MsTileInfo* __restrict__ tiles,
+                      unsigned long long* __restrict__ term_prefix, int64_t n_tiles, ms_scan_summary* __restrict__ out) {
+    const int tid = threadIdx.x;
+    __shared__ unsigned long long s_scan[RESOLVE_THREADS / 32];
+    __shared__ unsigned long long s_running, s_quotes, s_blank_total, s_acc;
+    __shared__ uint32_t s_flags;
+    __shared__ int s_ncand;
+    __shared__ long long s_cand[RESOLVE_CAND_CAP];
+
+    if (tid == 0) {
+        s_running = 0;
+        s_quotes = 0;
+        s_blank_total = 0;
+        s_flags = 0;
+        s_ncand = 0;
+    }
+    __syncthreads();
+
+    // ---- exclusive prefix of terminator counts
+    for (int64_t base = 0; base < n_tiles; base += RESOLVE_THREADS) {
+        int64_t k = base + tid;
+        unsigned long long v = k < n_tiles ? tiles[k].n_term : 0ull;
+        unsigned long long inc = v;
+        for (int o = 1; o < 32; o <<= 1) {
+            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+            if ((tid & 31) >= o) inc += t;
+        }
+        if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
+        __syncthreads();
+        unsigned long long wbase = 0;
+        for (int w = 0; w < (tid >> 5); w++) wbase += s_scan[w];
+        unsigned long long run = s_running;
+        if (k < n_tiles) term_prefix[k] = run + wbase + inc - v;
+        __syncthreads();
+        if (tid == RESOLVE_THREADS - 1) s_running = run + wbase + inc;
+        __syncthreads();
+    }
+    if (tid == 0) term_prefix[n_tiles] = s_running;
+
+    // ---- blank rows
+    unsigned long long my_quotes = 0, my_blank = 0;
+    uint32_t my_flags = 0;
+    for (int64_t k = tid; k < n_tiles; k += RESOLVE_THREADS) {
+        MsTileInfo ti = tiles[k];
+        my_quotes += ti.n_quotes;
+        if (ti.flags & MS_TI_HIGH) my_flags |= MS_SCAN_HAS_HIGH_BYTES;
+        if (ti.flags & MS_TI_OVERFLOW) my_flags |= MS_SCAN_BLANK_OVERFLOW;
+        if (ti.flags & MS_TI_HAS_CR) my_flags |= MS_SCAN_HAS_CR;
+        const int64_t t0 = k * (int64_t)MS_TILE_BYTES;
+        my_blank += ti.n_blank;
+        for (int i = 0; i < 2; i++) {
+            if (ti.blank_pos[i] >= 0) {
+                int slot = atomicAdd(&s_ncand, 1);
+                if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.blank_pos[i];
+            }
+        }
+        if (ti.flags & MS_TI_HAS_TERM) {
+            // the row ending at this tile's first terminator began in an earlier tile (or at
+            // the first byte of this one): walk back to the previous terminator
+            uint32_t acc = 0;
+            for (int64_t j = k - 1; j >= 0; j--) {
+                uint32_t f = tiles[j].flags;
+                acc |= f & MS_TI_NB_TAIL;
+                if (f & MS_TI_HAS_TERM) break;
+            }
+            if (!acc && !(ti.flags & MS_TI_NB_HEAD)) {
+                my_blank += 1;
+                int slot = atomicAdd(&s_ncand, 1);
+                if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.first_term;
+            }
+        }
+    }
+    // tiles with more than two decided blank rows: their 3rd.. positions are not recorded;
+    // harmless unless they are among the first MS_MAX_BLANK_ROWS of the file (flagged below)
+    if (my_quotes) atomicAdd(&s_quotes, my_quotes);
+    if (my_blank) atomicAdd(&s_blank_total, my_blank);
+    if (my_flags) atomicOr(&s_flags, my_flags);
+    __syncthreads();
+
+    // ---- unterminated last row
+    __shared__ int s_eof_row;
+    if (tid == 0) {
+        s_eof_row = 0;
+        if (n > 0) {
+            const MsTileInfo last = tiles[n_tiles - 1];
+            const int64_t t0 = (n_tiles - 1) * (int64_t)MS_TILE_BYTES;
+            bool ends_with_term = (last.flags & MS_TI_HAS_TERM) && (t0 + last.last_term == n - 1);
+            if (!ends_with_term) {
+                s_eof_row = 1;
+                uint32_t acc = 0;
+                for (int64_t j = n_tiles - 1; j >= 0; j--) {
+                    uint32_t f = tiles[j].flags;
+                    acc |= f & MS_TI_NB_TAIL;
+                    if (f & MS_TI_HAS_TERM) break;
+                }
+                if (!acc) {
+                    s_blank_total += 1;
+                    int slot = s_ncand++;
+                    if (slot < RESOLVE_CAND_CAP) s_cand[slot] = n;  // virtual terminator
+                }
+            }
+        }
+    }
+    __syncthreads();
+
+    // ---- order the candidates, keep the first MS_MAX_BLANK_ROWS
+    __shared__ int s_nrep;
+    if (tid == 0) {
+        int nc = s_ncand;
+        if (nc > RESOLVE_CAND_CAP) {
+            s_flags |= MS_SCAN_BLANK_OVERFLOW;
+            nc = RESOLVE_CAND_CAP;
+        }
+        for (int i = 1; i < nc; i++) {  // insertion sort, nc is tiny
+            long long x = s_cand[i];
+            int j = i - 1;
+            while (j >= 0 && s_cand[j] > x) {
+                s_cand[j + 1] = s_cand[j];
+                j--;
+            }
+            s_cand[j + 1] = x;
+        }
+        // a tile that decided more than two blank rows only recorded two: if one of the
+        // first MS_MAX_BLANK_ROWS candidates comes from such a tile the order is unreliable
+        int nrep = nc < MS_MAX_BLANK_ROWS ? nc : MS_MAX_BLANK_ROWS;
+        for (int i = 0; i < nrep; i++) {
+            long long p = s_cand[i];
+            int64_t k = p >= n ? n_tiles - 1 : p / MS_TILE_BYTES;
+            if (tiles[k].n_blank > 2) s_flags |= MS_SCAN_BLANK_OVERFLOW;
+        }
+        s_nrep = nrep;
+    }
+    __syncthreads();
+
+    // ---- csv row index of each reported blank row
+    const int nrep = s_nrep;
+    for (int i = 0; i < nrep; i++) {
+        const long long p = s_cand[i];
+        unsigned long long row;
+        if (p >= n) {
+            row = term_prefix[n_tiles];
+        } else {
+            const int64_t k = p / MS_TILE_BYTES;
+            unsigned long long c = ms_block_count_terms(src, n, k * (int64_t)MS_TILE_BYTES, p, &s_acc);
+            row = term_prefix[k] + c;
+        }
+        if (tid == 0) {
+            out->blank_row[i] = (int64_t)row;
+            out->blank_end[i] = p;
+        }
+        __syncthreads();
+    }
+    if (tid == 0) {
+        for (int i = nrep; i < MS_MAX_BLANK_ROWS; i++) {
+            out->blank_row[i] = -1;
+            out->blank_end[i] = -1;
+        }
+        out->n_bytes = n;
+        out->n_terminators = (int64_t)term_prefix[n_tiles];
+        out->n_rows = (int64_t)term_prefix[n_tiles] + s_eof_row;
+        out->n_quotes = (int64_t)s_quotes;
+        out->n_blank_rows = (int64_t)s_blank_total;
+        out->flags = s_flags;
+        out->n_reported = (uint32_t)nrep;
+    }
+}
+
+// ===================================================================================================
+// pass 2
+// ===================================================================================================
+#define PARSE_THREADS 512
+#define PARSE_WARPS (PARSE_THREADS / 32)
+#define PARSE_REGION (MS_TILE_BYTES + MS_MAX_ROW_BYTES)  // bytes staged per CTA
+#define PARSE_CHUNK (PARSE_REGION / PARSE_THREADS)        // 144 bytes per thread: 128 + 16 -> conflict-free LDS.128
+#define PARSE_SEGS (PARSE_CHUNK / 16)
+static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGION, "chunking");
+#define PARSE_PAD 16  // bytes staged before and after the region
+#define PARSE_SMEM (PARSE_REGION + 2 * PARSE_PAD)
+
+struct MsSectionsArg {
+    ms_section s[MS_MAX_SECTIONS];
+    int n;
+};
+
+struct MsScanElem {
+    int n_term;    // terminators in the span
+    int c_tail;    // commas after the last terminator of the span (all commas if none)
+    int has_term;
+    int last_delim;  // region offset of the last delimiter (comma / terminator) in the span, -1 if none
+};
+__device__ __forceinline__ MsScanElem ms_elem_combine(MsScanElem a, MsScanElem b) {
+    MsScanElem r;
+    r.n_term = a.n_term + b.n_term;
+    r.c_tail = b.has_term ? b.c_tail : a.c_tail + b.c_tail;
+    r.has_term = a.has_term | b.has_term;
+    r.last_delim = max(a.last_delim, b.last_delim);
+    return r;
+}
+__device__ __forceinline__ MsScanElem ms_elem_shfl_up(MsScanElem e, int d) {
+    MsScanElem r;
+    r.n_term = __shfl_up_sync(0xffffffffu, e.n_term, d);
+    r.c_tail = __shfl_up_sync(0xffffffffu, e.c_tail, d);
+    r.has_term = __shfl_up_sync(0xffffffffu, e.has_term, d);
+    r.last_delim = __shfl_up_sync(0xffffffffu, e.last_delim, d);
+    return r;
+}
+
+struct MsParsed {
+    uint64_t bits;
+    int status;
+};
+// One out-of-line copy of the field parser: the walk below is unrolled per 16-byte segment.
+__device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uint8_t* e) {
+    MsParsed r;
+    r.bits = MS_NAN_BITS;
+    r.status = ms_parse_field(s, e, &r.bits);
+    return r;
+}
+
+struct MsRowCtx {  // where the fields of the current row go
+    double* out;   // &d_out[row - row_begin], NULL when the row is not a data row of this CTA
+    int64_t stride;
+    int num_cols, n_keep;
+};
+
+__device__ __forceinline__ MsRowCtx ms_row_ctx(const MsSectionsArg& secs, long long row, bool owned) {
+    MsRowCtx c;
+    c.out = nullptr;
+    c.stride = 0;
+    c.num_cols = 0;
+    c.n_keep = 0;
+    if (owned) {
+#pragma unroll
+        for (int i = 0; i < MS_MAX_SECTIONS; i++) {
+            if (i < secs.n && row >= secs.s[i].row_begin && row < secs.s[i].row_end) {
+                c.out = secs.s[i].d_out + (row - secs.s[i].row_begin);
+                c.stride = secs.s[i].stride;
+                c.num_cols = secs.s[i].num_cols;
+                c.n_keep = secs.s[i].n_keep;
+            }
+        }
+    }
+    return c;
+}
+
+__global__ void __launch_bounds__(PARSE_THREADS)
+    ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
+                    const MsSectionsArg secs, unsigned long long* __restrict__ status) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
+    __shared__ MsScanElem s_warp[PARSE_WARPS];
+    __shared__ int s_lt_end, s_total_terms;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int64_t tile = blockIdx.x;
+    const int64_t t0 = tile * (int64_t)MS_TILE_BYTES;
+    const int tile_len = (int)min((int64_t)MS_TILE_BYTES, n - t0);
+
+    // rows of this tile that can be data rows at all?  (cheap early exit for header-only tiles)
+    const unsigned long long row_lo = term_prefix[tile], row_hi = term_prefix[tile + 1] + 1;
+    bool any = false;
+    for (int i = 0; i < secs.n; i++)
+        if ((long long)row_hi >= secs.s[i].row_begin && (long long)row_lo < secs.s[i].row_end) any = true;
+    if (!any) return;
+
+    // ---- stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
+    for (int i = tid; i < PARSE_SMEM / 16; i += PARSE_THREADS) {
+        int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
+        uint4 v;
+        if (off < 0)
+            v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        else
+            v = ms_load16(src, off, n, 0x0a0a0a0au);
+        *reinterpret_cast<uint4*>(smem_raw + i * 16) = v;
+    }
+    __syncthreads();
+
+    // ---- delimiter masks of my chunk, kept in registers
+    const int c0 = tid * PARSE_CHUNK;
+    uint32_t mterm[PARSE_SEGS], mcomma[PARSE_SEGS];
+    MsScanElem mine;
+    mine.n_term = 0;
+    mine.c_tail = 0;
+    mine.has_term = 0;
+    mine.last_delim = -1;
+    int lt_end_part = -1;  // terminators of my chunk before position tile_len - 1, if it is mine
+#pragma unroll
+    for (int s = 0; s < PARSE_SEGS; s++) {
+        const int p0 = c0 + s * 16;
+        uint4 v = *reinterpret_cast<const uint4*>(reg + p0);
+        MsDelims d = ms_delims16(v);
+        uint32_t next_lf = reg[p0 + 16] == '\n';
+        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
+        mterm[s] = term;
+        mcomma[s] = d.comma;
+        if (term) {
+            int hi = 31 - __clz(term);
+            mine.c_tail = __popc(d.comma >> (hi + 1));
+            mine.has_term = 1;
+        } else {
+            mine.c_tail += __popc(d.comma);
+        }
+        mine.n_term += __popc(term);
+        uint32_t dl = term | d.comma;
+        if (dl) mine.last_delim = p0 + 31 - __clz(dl);
+    }
+    // terminators strictly before region offset tile_len - 1 decide which rows start inside the tile
+    {
+        const int q = tile_len - 1;
+        if (q >= c0 && q < c0 + PARSE_CHUNK) {
+            int cnt = 0;
+#pragma unroll
+            for (int s = 0; s < PARSE_SEGS; s++) {
+                const int p0 = c0 + s * 16;
+                if (q >= p0 + 16)
+                    cnt += __popc(mterm[s]);
+                else if (q > p0)
+                    cnt += __popc(mterm[s] & ((1u << (q - p0)) - 1u));
+            }
+            lt_end_part = cnt;
+        }
+    }
+
+    // ---- block-wide exclusive scan
+    MsScanElem inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        MsScanElem o = ms_elem_shfl_up(inc, d);
+        if (lane >= d) inc = ms_elem_combine(o, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    MsScanElem before;  // everything before my warp
+    before.n_term = 0;
+    before.c_tail = 0;
+    before.has_term = 0;
+    before.last_delim = -1;
+    for (int w = 0; w < warp; w++) before = ms_elem_combine(before, s_warp[w]);
+    MsScanElem prev_lane = ms_elem_shfl_up(inc, 1);
+    MsScanElem excl = lane == 0 ? before : ms_elem_combine(before, prev_lane);
+    if (lt_end_part >= 0) s_lt_end = excl.n_term + lt_end_part;
+    if (tid == PARSE_THREADS - 1) s_total_terms = excl.n_term + mine.n_term;
+    __syncthreads();
+
+    // ---- ownership: rows that START in [t0, t0 + tile_len)
+    // local row index lt = terminators in [t0, position); row lt starts right after the lt-th one
+    const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
+    const int lt_first = starts_at_t0 ? 0 : 1;
+    const int lt_last = s_lt_end;  // inclusive
+    if (lt_last >= lt_first && s_total_terms < lt_last + 1) {
+        // the last owned row does not end inside the staged region
+        if (tid == 0) atomicMin(status, ((unsigned long long)t0 << 3) | MS_ERR_KIND_ROW_TOO_LONG);
+        return;
+    }
+
+    // ---- walk my chunk: every delimiter ends a field
+    int lt = excl.n_term;
+    int col = excl.c_tail;
+    int fs = excl.last_delim + 1;  // start of the field in progress
+    bool owned = lt >= lt_first && lt <= lt_last;
+    MsRowCtx ctx = ms_row_ctx(secs, (long long)row_lo + lt, owned);
+    if (lt > lt_last) return;  // whole chunk belongs to the next tile
+
+#pragma unroll
+    for (int s = 0; s < PARSE_SEGS; s++) {
+        const int p0 = c0 + s * 16;
+        uint32_t term = mterm[s], comma = mcomma[s];
+        uint32_t dl = term | comma;
+        if (!dl) continue;
+        if (!term && (ctx.out == nullptr || col >= ctx.num_cols)) {
+            // nothing to parse here: only commas of a row we skip or of its ignored tail
+            col += __popc(comma);
+            fs = p0 + 32 - __clz(dl);
+            continue;
+        }
+        while (dl) {
+            const int b = __ffs(dl) - 1;
+            dl &= dl - 1u;
+            const int p = p0 + b;
+            const bool is_term = (term >> b) & 1u;
+            if (ctx.out != nullptr && col < ctx.num_cols) {
+                int fe = p;
+                if (is_term && fe > fs && reg[fe - 1] == '\r') fe--;
+                uint64_t bits = MS_NAN_BITS;
+                if (fe > fs) {
+                    MsParsed pr = ms_parse_field_call(reg + fs, reg + fe);
+                    bits = pr.bits;
+                    if (pr.status != MS_PARSE_OK) {
+                        bits = MS_NAN_BITS;
+                        atomicMin(status,
+                                  ((unsigned long long)(t0 + fs) << 3) |
+                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+                    }
+                }
+                const int ch = col - 2;
+                if (ch >= 0 && ch < ctx.n_keep) ctx.out[(int64_t)ch * ctx.stride] = ms_bits_to_double(bits);
+            }
+            if (is_term) {
+                // short row: the cells it does not have are NaN (pandas pads ragged rows)
+                if (ctx.out != nullptr) {
+                    for (int c = max(col + 1, 2); c < ctx.num_cols; c++) {
+                        const int ch = c - 2;
+                        if (ch < ctx.n_keep) ctx.out[(int64_t)ch * ctx.stride] = ms_bits_to_double(MS_NAN_BITS);
+                    }
+                }
+                lt++;
+                col = 0;
+                if (lt > lt_last) return;
+                owned = lt >= lt_first;
+                ctx = ms_row_ctx(secs, (long long)row_lo + lt, owned);
+            } else {
+                col++;
+            }
+            fs = p + 1;
+        }
+    }
+}
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+extern "C" int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+                       ms_scan_summary* d_summary, void* stream) {
+    if (!d_bytes || !d_workspace || !d_summary || n_bytes < 0) return MS_E_INVALID;
+    if (((uintptr_t)d_bytes & 15) != 0) return MS_E_INVALID;
+    if (workspace_bytes < ms_workspace_bytes(n_bytes)) return MS_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int64_t n_tiles = ms_num_tiles(n_bytes);
+    MsWorkspaceView v = ms_view(d_workspace, ms_num_tiles(n_bytes < 1 ? 1 : n_bytes));
+    if (n_tiles > 0) {
+        ms_scan_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles);
+        MS_COUNT_LAUNCH();
+        MS_CUDA_CHECK(cudaGetLastError());
+    }
+    ms_resolve_kernel<<<1, RESOLVE_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.term_prefix, n_tiles, d_summary);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}
+
+extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
+                        int32_t n_sections, uint64_t* d_status, void* stream) {
+    if (!d_bytes || !d_workspace || !d_status || n_bytes < 0) return MS_E_INVALID;
+    if (n_sections < 0 || n_sections > MS_MAX_SECTIONS || (n_sections > 0 && !h_sections)) return MS_E_INVALID;
+    if (((uintptr_t)d_bytes & 15) != 0) return MS_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA_CHECK(cudaMemsetAsync(d_status, 0xFF, sizeof(uint64_t), st));
+    const int64_t n_tiles = ms_num_tiles(n_bytes);
+    MsSectionsArg arg;
+    memset(&arg, 0, sizeof arg);
+    arg.n = 0;
+    for (int i = 0; i < n_sections; i++) {
+        const ms_section& s = h_sections[i];
+        if (s.row_end <= s.row_begin || s.num_cols <= 0) continue;  // nothing to parse
+        if (!s.d_out && s.n_keep > 0) return MS_E_INVALID;
+        if (s.stride < s.row_end - s.row_begin || s.n_keep < 0 || s.n_keep > s.num_cols) return MS_E_INVALID;
+        arg.s[arg.n++] = s;
+    }
+    if (n_tiles == 0 || arg.n == 0) return MS_OK;
+    MS_CUDA_CHECK(cudaFuncSetAttribute(ms_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PARSE_SMEM));
+    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), n_tiles);
+    ms_parse_kernel<<<(unsigned)n_tiles, PARSE_THREADS, PARSE_SMEM, st>>>(d_bytes, n_bytes, v.term_prefix, arg,
+                                                                           (unsigned long long*)d_status);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}

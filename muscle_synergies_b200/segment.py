@@ -1,0 +1,276 @@
+"""Trial windowing on the GPU: drop-in for the compute part of the reference's project/segment.py.
+
+    Phase / Trecho / Cycle          segment.py:21-87
+    reactions                       segment.py:118-121
+    Segmenter                       segment.py:124-298   (same methods and argument forms)
+    _transition_indices             segment.py:667-755   -> CUDA (ms_find_transitions)
+    _organize_transitions           segment.py:787-917   -> 40 ints -> 32 (frame, subframe) slices, host
+
+plus `Segmenter.cut`, which gathers any set of windows from a device's channel-major block
+with one kernel launch (ms_cut_windows) instead of one `df.iloc[...]` per window.
+
+The plotting half of the reference file (SegmentPlotter, :301-664) is out of scope.
+
+Behavioural note: when the signal holds fewer than `num_segments`
+alternations the reference silently re-appends a stale index (:745-752); this implementation
+raises ValueError instead.  Parity is claimed only when all transitions exist.
+"""
+import ctypes
+from collections import OrderedDict
+from enum import Enum, auto
+from typing import List, Mapping, Optional, Sequence, Tuple, Union
+
+from . import _native as nat
+from .vicon_data.data_model import DeviceData, FrameSubfr, ViconNexusData
+from .vicon_data.definitions import DeviceType  # noqa: F401  (re-exported like the reference)
+
+
+class Phase(Enum):
+    DAA = "DAA"
+    AS = "AS"
+    DAE = "DAE"
+    BL = "BL"
+
+    @staticmethod
+    def from_str(phase: str) -> "Phase":
+        return {"DAA": Phase.DAA, "DAE": Phase.DAE, "AS": Phase.AS, "BL": Phase.BL}[phase.upper()]
+
+
+class Trecho(Enum):
+    FIRST = auto()
+    SECOND = auto()
+    THIRD = auto()
+    FOURTH = auto()
+
+
+class Cycle(Enum):
+    FIRST = auto()
+    SECOND = auto()
+
+
+Segments = Mapping[Trecho, Mapping[Cycle, Mapping[Phase, slice]]]
+PhaseRef = Union[Phase, int, str]
+
+
+def reactions(vicon_nexus_data: ViconNexusData):
+    """Vertical ground reaction of the two force plates as pandas Series (segment.py:118-121)."""
+    left_fp, right_fp = vicon_nexus_data.forcepl
+    return left_fp.df["Fz"], right_fp.df["Fz"]
+
+
+def _fz_tensor(dev: DeviceData):
+    """The Fz channel of a force plate as a CUDA view (what df["Fz"] selects)."""
+    coords = list(dev._coords)
+    if coords.count("Fz") != 1:
+        raise KeyError("Fz")
+    return dev.tensor[coords.index("Fz")]
+
+
+def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments: int = 40, with_loaded=False):
+    """_transition_indices (segment.py:667-755) on two CUDA float64 vectors.
+
+    Returns a list of python ints (and, with_loaded, which plates are loaded at each index:
+    bit 0 left, bit 1 right).  Raises ValueError when fewer than num_segments exist
+    (num_segments=0 keeps the reference meaning "as many as there are").
+    """
+    import torch
+
+    lib = nat.lib()
+    if not (left_fz.is_cuda and right_fz.is_cuda):
+        raise nat.NativeError("transition_indices needs CUDA tensors; there is no CPU fallback")
+    left_fz = left_fz.contiguous()
+    right_fz = right_fz.contiguous()
+    if left_fz.dtype != torch.float64 or right_fz.dtype != torch.float64 or left_fz.shape != right_fz.shape:
+        raise ValueError("left/right reactions must be float64 vectors of equal length")
+    n = int(left_fz.numel())
+    dev = left_fz.device
+    want = num_segments if num_segments > 0 else max(1, n)
+    work = torch.empty(int(lib.ms_transitions_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+    out = torch.empty(want, dtype=torch.int64, device=dev)
+    loaded = torch.empty(want, dtype=torch.int32, device=dev)
+    found = torch.zeros(1, dtype=torch.int32, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    nat.check(
+        lib.ms_find_transitions(
+            left_fz.data_ptr(), right_fz.data_ptr(), n, int(min_phase_size), int(want), work.data_ptr(),
+            out.data_ptr(), loaded.data_ptr(), found.data_ptr(), ctypes.c_void_p(stream.cuda_stream),
+        ),
+        "ms_find_transitions",
+    )
+    k = int(found.item())
+    if num_segments > 0 and k < num_segments:
+        legs = 1 if k % 2 == 0 else 2
+        raise ValueError(
+            f"no phase found with {min_phase_size} adjacent measurements with {legs} leg(s) with a nonzero reaction"
+            f" (found {k} of {num_segments} transitions)"
+        )
+    idx = out[:k].tolist()
+    if with_loaded:
+        return idx, loaded[:k].tolist()
+    return idx
+
+
+def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequence[int]) -> Segments:
+    """_organize_transitions (segment.py:787-917): 40 indices -> 4 trechos x 2 cycles x 4 phases."""
+
+    def single_leg_phase_type(pos: int) -> Phase:
+        flags = loaded[pos]
+        if flags == 3 or flags == 0:
+            raise ValueError(
+                "expected index corresponding to a phase in which there is ground reaction for exactly one leg."
+            )
+        return Phase.BL if flags & 1 else Phase.AS
+
+    def phase_seq(second_phase: Phase, trecho: Trecho) -> List[Phase]:
+        if trecho in (Trecho.FIRST, Trecho.THIRD):
+            if second_phase is Phase.BL:
+                return [Phase.DAA, Phase.BL, Phase.DAE, Phase.AS]
+            return [Phase.DAE, Phase.AS, Phase.DAA, Phase.BL]
+        if second_phase is Phase.BL:
+            return [Phase.DAE, Phase.BL, Phase.DAA, Phase.AS]
+        return [Phase.DAA, Phase.AS, Phase.DAE, Phase.BL]
+
+    def cycle_dict(names, bounds):
+        slices = [slice(to_framesubfr(bounds[i]), to_framesubfr(bounds[i + 1] - 1)) for i in range(len(bounds) - 1)]
+        return OrderedDict(zip(names, slices))
+
+    segments = {}
+    for n, trecho in enumerate(Trecho):
+        starts = list(transitions[10 * n + 1 : 10 * n + 9])
+        end = transitions[10 * n + 9]
+        names = phase_seq(single_leg_phase_type(10 * n + 2), trecho)
+        segments[trecho] = {
+            Cycle.FIRST: cycle_dict(names, starts[:5]),
+            Cycle.SECOND: cycle_dict(names, starts[4:] + [end]),
+        }
+    return segments
+
+
+class Segmenter:
+    """Segments a trial into trechos, cycles and phases from the two force plates."""
+
+    def __init__(self, data: ViconNexusData, min_phase_size: int = 10, num_segments: int = 40):
+        left_fp, right_fp = data.forcepl  # exactly two plates, like reactions()
+        self._data = data
+        self.transitions, self._loaded = transition_indices(
+            _fz_tensor(left_fp), _fz_tensor(right_fp), min_phase_size, num_segments, with_loaded=True
+        )
+        self._segments = organize_transitions(left_fp.to_framesubfr, self.transitions, self._loaded)
+
+    # ---- reference API ------------------------------------------------------------------------
+    def ith_phase(self, trecho: Union[Trecho, int], i: int) -> Phase:
+        if i not in range(1, 5):
+            raise IndexError("i should be a number between 1 and 4")
+        trecho = self._parse_trecho(trecho)
+        return tuple(self._segments[trecho][Cycle.FIRST].keys())[(i - 1) % 4]
+
+    def get_times_of(self, trecho, cycle=None, phase=None) -> slice:
+        trecho, cycle, phase = self._parse_segment_args(trecho, cycle, phase)
+        if phase is not None:
+            return self._segments[trecho][cycle][phase]
+        if cycle is not None:
+            return self._times_of_cycle(trecho, cycle)
+        first = self._times_of_cycle(trecho, Cycle.FIRST)
+        second = self._times_of_cycle(trecho, Cycle.SECOND)
+        return slice(first.start, second.stop)
+
+    def _times_of_cycle(self, trecho: Trecho, cycle: Cycle) -> slice:
+        phases = tuple(self._segments[trecho][cycle].values())
+        return slice(phases[0].start, phases[3].stop)
+
+    def _parse_segment_args(self, trecho, cycle, phase_ref):
+        def must_be_omitted(given: bool):
+            if given:
+                raise ValueError(
+                    "the optional arguments should be ommitted if a (trecho, cycle, phase_ref) triple is given"
+                )
+
+        if phase_ref is not None and cycle is None:
+            raise ValueError("if a phase is given, a cycle should also be")
+        given = cycle is not None or phase_ref is not None
+        try:
+            trecho, cycle, phase_ref = trecho
+        except TypeError:
+            pass
+        except ValueError:
+            trecho, cycle = trecho
+            must_be_omitted(given)
+        else:
+            must_be_omitted(given)
+        trecho = self._parse_trecho(trecho)
+        cycle = self._parse_cycle(cycle)
+        return trecho, cycle, self._parse_phase(trecho, phase_ref)
+
+    @staticmethod
+    def _parse_trecho(trecho: Union[Trecho, int]) -> Trecho:
+        # ints are 1-based positions (the reference's intent; its `trecho in Trecho` test
+        # only behaves that way on Python <= 3.7)
+        if isinstance(trecho, Trecho):
+            return trecho
+        return tuple(Trecho)[trecho - 1]
+
+    @staticmethod
+    def _parse_cycle(cycle: Optional[Union[Cycle, int]] = None) -> Optional[Cycle]:
+        if cycle is None or isinstance(cycle, Cycle):
+            return cycle
+        return tuple(Cycle)[cycle - 1]
+
+    def _parse_phase(self, trecho: Trecho, phase_ref: Optional[PhaseRef]) -> Optional[Phase]:
+        if phase_ref is None or isinstance(phase_ref, Phase):
+            return phase_ref
+        try:
+            return Phase.from_str(phase_ref)
+        except (KeyError, AttributeError):
+            pass
+        return self.ith_phase(trecho, phase_ref)
+
+    # ---- GPU window gather ----------------------------------------------------------------------
+    def all_phase_windows(self) -> List[Tuple[Trecho, Cycle, Phase, slice]]:
+        out = []
+        for trecho, cycles in self._segments.items():
+            for cycle, phases in cycles.items():
+                for phase, sl in phases.items():
+                    out.append((trecho, cycle, phase, sl))
+        return out
+
+    @staticmethod
+    def cut(device: DeviceData, windows: Sequence[slice]):
+        """Rows `device[w]` for every (frame, subframe) slice w, gathered on the GPU.
+
+        Returns a list of (n_columns, n_rows_w) float64 CUDA tensors (channel-major), the
+        same rows `device.df.iloc[device.to_index(w)]` selects (exclusive stop)."""
+        return cut_windows(device, [device.to_index(w) for w in windows])
+
+
+def cut_windows(device: DeviceData, index_slices: Sequence[slice]):
+    """Batched `df.iloc[a:b]` on the device-resident block of one DeviceData."""
+    import torch
+
+    lib = nat.lib()
+    src = device.tensor
+    n_rows = int(src.shape[1])
+    n_ch = int(src.shape[0])
+    starts, stops = [], []
+    for sl in index_slices:
+        if sl.step not in (None, 1):
+            raise ValueError("cut_windows supports unit-step slices only")
+        a, b, _ = sl.indices(n_rows)
+        starts.append(a)
+        stops.append(max(a, b))
+    lens = [b - a for a, b in zip(starts, stops)]
+    offsets = [0]
+    for ln in lens:
+        offsets.append(offsets[-1] + ln * n_ch)
+    dev = src.device
+    meta = torch.tensor([starts, stops, offsets[:-1]], dtype=torch.int64).to(dev, non_blocking=False)
+    out = torch.empty(max(1, offsets[-1]), dtype=torch.float64, device=dev)
+    stream = torch.cuda.current_stream(dev)
+    if index_slices and n_ch:
+        nat.check(
+            lib.ms_cut_windows(
+                src.data_ptr(), int(src.stride(0)), n_ch, meta[0].data_ptr(), meta[1].data_ptr(), meta[2].data_ptr(),
+                len(lens), out.data_ptr(), max(lens) if lens else 0, ctypes.c_void_p(stream.cuda_stream),
+            ),
+            "ms_cut_windows",
+        )
+    return [out[offsets[i] : offsets[i + 1]].view(n_ch, lens[i]) for i in range(len(lens))]

@@ -1,0 +1,329 @@
+"""What load_vicon_file returns: the reference's user-facing data model over GPU-resident arrays.
+
+API mirror of src/muscle_synergies/vicon_data/user_data.py: ViconNexusData (:42-301),
+frame trackers (:483-661), DeviceData (:664-772) - same attribute names, index math and
+exceptions.  Differences, all additive:
+
+  * the arrays live in HBM as one channel-major float64 block per CSV section
+    (`SectionBlock`); `DeviceData.tensor` is a zero-copy (channels, rows) view of it;
+  * `DeviceData.df` is built lazily from a pinned host copy of the block, which has the
+    memory layout pandas itself ends up with for the reference (user_data.py:396).
+"""
+from functools import lru_cache
+from typing import Optional, Sequence, Tuple, Union
+
+import numpy as np
+import pandas as pd
+
+from .definitions import DeviceType, SamplingFreq
+
+FrameSubfr = Tuple[int, int]
+
+
+class SectionBlock:
+    """Channel-major float64 block of one CSV section: tensor[channel, row]."""
+
+    def __init__(self, tensor, n_rows: int):
+        self.tensor = tensor  # torch.float64, (n_keep, stride) on the GPU, stride >= n_rows
+        self.n_rows = n_rows
+        self._host = None
+
+    def host(self) -> np.ndarray:
+        """(n_keep, n_rows) float64 numpy array (one device->host copy, cached)."""
+        if self._host is None:
+            import torch
+
+            view = self.tensor[:, : self.n_rows]
+            pinned = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
+            pinned.copy_(view, non_blocking=False)
+            self._host = pinned.numpy()
+        return self._host
+
+
+class ViconNexusData:
+    """The data of one Vicon Nexus CSV file, grouped by device type."""
+
+    def __init__(self, forcepl: Sequence["DeviceData"], emg: "DeviceData", traj: Sequence["DeviceData"]):
+        self.forcepl = forcepl
+        self.emg = emg
+        self.traj = traj
+
+    def __getitem__(self, device_type: Union[DeviceType, str]):
+        device_type = self._parse_device_type(device_type)
+        if device_type is DeviceType.FORCE_PLATE:
+            return self.forcepl
+        if device_type is DeviceType.EMG:
+            return self.emg
+        if device_type is DeviceType.TRAJECTORY_MARKER:
+            return self.traj
+        raise KeyError(f"device type not understood: {device_type}")
+
+    def get_cols(self, device_type, device_inds: Optional[Sequence[int]] = None, time=None, cols=None):
+        def one(dev: "DeviceData"):
+            frame = dev.df if time is None else dev[time]
+            return frame[cols]
+
+        device_type = self._parse_device_type(device_type)
+        if device_type is DeviceType.EMG:
+            return one(self.emg)
+        devices = self[device_type]
+        if device_inds is not None:
+            devices = [devices[i] for i in device_inds]
+        return tuple(one(dev) for dev in devices)
+
+    def plot_cols(self, device_type, col, device_inds=None, time=None, labels=None, show=True, **kwargs):
+        import matplotlib.pyplot as plt  # plotting is outside the accelerated path
+
+        fig, ax = plt.subplots()
+        series = self.get_cols(device_type, device_inds=device_inds, time=time, cols=col)
+        if self._parse_device_type(device_type) is DeviceType.EMG:
+            series = (series,)
+        if labels is None:
+            labels = [None] * len(series)
+        for label, current in zip(labels, series):
+            ax.plot(self.time_seq(device_type), current, label=label, **kwargs)
+        if show:
+            plt.show()
+            return None
+        return fig, ax
+
+    def sampling_frequency(self, device_type) -> int:
+        return self._get_device_of_type(device_type).sampling_frequency
+
+    def time_seq(self, device_type) -> pd.Series:
+        return self._get_device_of_type(self._parse_device_type(device_type)).time_seq()
+
+    def to_framesubfr(self, device_type, index):
+        return self._get_device_of_type(device_type).to_framesubfr(index)
+
+    def to_index(self, device_type, frame, subframe: Optional[int] = None):
+        return self._get_device_of_type(device_type).to_index(frame, subframe)
+
+    def _get_device_of_type(self, device_type) -> "DeviceData":
+        if self._parse_device_type(device_type) is DeviceType.EMG:
+            return self.emg
+        return self[device_type][0]
+
+    @staticmethod
+    def _parse_device_type(device_type):
+        try:
+            return DeviceType.from_str(device_type)
+        except AttributeError:
+            return device_type
+
+    def __repr__(self):
+        return "ViconNexusData(forcepl=[...], emg=<DeviceData>, traj=[...])"
+
+    def describe(self) -> str:
+        def amount(num, noun):
+            return f"{num} {noun}{'' if num == 1 else 's'}"
+
+        def members(seq):
+            seq = list(seq)
+            if len(seq) > 2:
+                seq = [seq[0], "...", seq[-1]]
+            return ", ".join(map(str, seq))
+
+        return (
+            "ViconNexusData:\n"
+            f"+ emg: {amount(len(self.emg.df.columns), 'column')}\n"
+            f"+ forcepl ({amount(len(self.forcepl), 'device')}): {members(self.forcepl)}\n"
+            f"+ traj ({amount(len(self.traj), 'device')}): {members(self.traj)}"
+        )
+
+
+class _SectionFrameTracker:
+    """(frame, subframe) <-> row index for one section (user_data.py:483-623)."""
+
+    def __init__(self, sampling_freq: SamplingFreq):
+        self._sampling_freq = sampling_freq
+
+    @property
+    def num_frames(self) -> int:
+        return self._sampling_freq.num_frames
+
+    @property
+    def num_subframes(self) -> int:
+        return self._sampling_freq.num_subframes
+
+    @property
+    def sampling_frequency(self) -> int:
+        raise NotImplementedError
+
+    @property
+    def final_index(self) -> int:
+        raise NotImplementedError
+
+    def _to_index(self, framesubfr: FrameSubfr) -> int:
+        raise NotImplementedError
+
+    def _to_framesubfr(self, index: int) -> FrameSubfr:
+        raise NotImplementedError
+
+    def to_index(self, frame, subframe):
+        if subframe is None:
+            if isinstance(frame, slice):
+                self._validate_slice(frame, self._validate_framesubfr_args)
+                return self._map_slice(frame, self._to_index)
+            frame, subframe = frame
+            return self._to_index((frame, subframe))
+        self._validate_framesubfr_args((frame, subframe))
+        return self._to_index((frame, subframe))
+
+    def to_framesubfr(self, index):
+        if isinstance(index, slice):
+            self._validate_slice(index, self._validate_index_arg)
+            return self._map_slice(index, self._to_framesubfr)
+        self._validate_index_arg(index)
+        return self._to_framesubfr(index)
+
+    def _validate_index_arg(self, index: int):
+        if index not in range(self.final_index + 1):
+            raise IndexError(f"index {index} out of bounds (max is self.final_index)")
+
+    def _validate_framesubfr_args(self, framesubfr: FrameSubfr):
+        frame, subframe = framesubfr
+        if frame not in range(1, self.num_frames + 1):
+            raise IndexError(f"frame {frame} is out of bounds")
+        if subframe not in range(self.num_subframes):
+            raise IndexError(f"subframe {subframe} out of range")
+
+    @staticmethod
+    def _validate_slice(slice_, validate):
+        validate(slice_.stop)
+        for arg in {slice_.start, slice_.step}:
+            if arg is not None:
+                validate(arg)
+
+    @staticmethod
+    def _map_slice(slice_, func):
+        def maybe(arg):
+            return None if arg is None else func(arg)
+
+        return slice(maybe(slice_.start), maybe(slice_.stop), maybe(slice_.step))
+
+    def time_seq(self) -> pd.Series:
+        return self._time_seq(self.sampling_frequency, self.final_index + 1)
+
+    @staticmethod
+    @lru_cache(maxsize=2)
+    def _time_seq(sampling_frequency: int, num_measurements: int) -> pd.Series:
+        period = 1 / sampling_frequency
+        return pd.Series(period * np.arange(1, num_measurements + 1, 1))
+
+
+class ForcesEMGFrameTracker(_SectionFrameTracker):
+    @property
+    def sampling_frequency(self) -> int:
+        return self._sampling_freq.freq_forces_emg
+
+    def _to_index(self, framesubfr):
+        frame, subframe = framesubfr
+        return (frame - 1) * self.num_subframes + subframe
+
+    def _to_framesubfr(self, index):
+        return (index // self.num_subframes) + 1, index % self.num_subframes
+
+    @property
+    def final_index(self) -> int:
+        return self.num_frames * self.num_subframes - 1
+
+
+class TrajFrameTracker(_SectionFrameTracker):
+    @property
+    def sampling_frequency(self) -> int:
+        return self._sampling_freq.freq_traj
+
+    def _to_index(self, framesubfr):
+        frame, _subframe = framesubfr
+        return frame - 1
+
+    def _to_framesubfr(self, index):
+        return index + 1, 0
+
+    @property
+    def final_index(self) -> int:
+        return self.num_frames - 1
+
+
+class DeviceData:
+    """Data of one measurement device (user_data.py:664-772)."""
+
+    def __init__(
+        self,
+        device_name: str,
+        device_type: DeviceType,
+        units,
+        frame_tracker: _SectionFrameTracker,
+        dataframe: Optional[pd.DataFrame] = None,
+        *,
+        block: Optional[SectionBlock] = None,
+        first_channel: int = 0,
+        coords: Optional[Sequence[str]] = None,
+    ):
+        self.name = device_name
+        self.dev_type = device_type
+        self.units = tuple(units)
+        self._frame_tracker = frame_tracker
+        self._df = dataframe
+        self._block = block
+        self._first_channel = first_channel
+        self._coords = list(coords) if coords is not None else (list(dataframe.columns) if dataframe is not None else [])
+
+    # ---- arrays -------------------------------------------------------------------------
+    @property
+    def tensor(self):
+        """(n_columns, n_rows) float64 CUDA tensor: a view of the section block, channel-major."""
+        if self._block is None:
+            raise AttributeError("this DeviceData was not produced by the CUDA loader")
+        c0 = self._first_channel
+        return self._block.tensor[c0 : c0 + len(self._coords), : self._block.n_rows]
+
+    @property
+    def values_cm(self) -> np.ndarray:
+        """(n_columns, n_rows) host array, channel-major (the block layout of `df`)."""
+        c0 = self._first_channel
+        return self._block.host()[c0 : c0 + len(self._coords)]
+
+    @property
+    def df(self) -> pd.DataFrame:
+        if self._df is None:
+            self._df = pd.DataFrame(self.values_cm.T, columns=self._coords, dtype=float)
+        return self._df
+
+    @df.setter
+    def df(self, value):
+        self._df = value
+
+    # ---- reference API --------------------------------------------------------------------
+    @property
+    def sampling_frequency(self) -> int:
+        return self._frame_tracker.sampling_frequency
+
+    def time_seq(self) -> pd.Series:
+        return self._frame_tracker.time_seq()
+
+    def __getitem__(self, indices):
+        if isinstance(indices, slice):
+            return self.df.iloc[self.to_index(indices)]
+        return self.df.iloc[self.to_index(*indices)]
+
+    def to_framesubfr(self, index):
+        return self._frame_tracker.to_framesubfr(index)
+
+    def to_index(self, frame, subframe: Optional[int] = None):
+        return self._frame_tracker.to_index(frame, subframe)
+
+    def __eq__(self, other) -> bool:
+        return (
+            self.name == other.name
+            and self.dev_type == other.dev_type
+            and self.units == other.units
+            and self.df.equals(other.df)
+        )
+
+    def __str__(self):
+        return f'DeviceData("{self.name}")'
+
+    def __repr__(self):
+        return f"<{str(self)}>"

@@ -1,0 +1,434 @@
+"""load_vicon_file on B200: host glue around the CUDA scan / parse kernels.
+
+Drop-in for the reference's `load_vicon_file(csv_filename) -> ViconNexusData`
+(src/muscle_synergies/vicon_data/load_csv.py:96-135).  Flow per file:
+
+  1. file bytes -> pinned host buffer -> HBM (one async copy);
+  2. ms_scan (CUDA): row terminators, blank (section separator) rows, quote count;
+  3. host: the 2 x 5 header lines (a few KB) through `HeaderMachine`, which applies the
+     reference's header rules (header.py);
+  4. ms_parse (CUDA): every data row of both sections -> channel-major float64 blocks in HBM,
+     bit-identical to float() per field;
+  5. host: wrap the blocks in ViconNexusData / DeviceData (DataFrames are built lazily).
+
+Errors: the kernels report the byte offset of the first field float() would reject; the host
+replays the reference's rule on that single row to raise the same
+`RuntimeError("error parsing line i of file f: ...")` chained to the same cause.
+
+There is no CPU data path: without a CUDA device or without libms_b200.so every entry
+point raises.
+"""
+import ctypes
+import os
+import re
+from typing import Callable, List, Optional, Tuple
+
+import numpy as np
+
+from .. import _native as nat
+from .data_model import (
+    DeviceData,
+    ForcesEMGFrameTracker,
+    SectionBlock,
+    TrajFrameTracker,
+    ViconNexusData,
+)
+from .definitions import DeviceType, SamplingFreq, SectionType
+from .header import (
+    HeaderMachine,
+    SectionLayout,
+    file_encoding,
+    replay_data_row,
+    rows_from_bytes,
+    wrap_error,
+)
+
+_TERMINATOR = re.compile(rb"\r\n|\r|\n")
+_HEADER_LINES = 5
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise nat.NativeError("muscle_synergies_b200 needs a CUDA device (B200, sm_100a); there is no CPU fallback")
+    return torch
+
+
+def _pad16(n: int) -> int:
+    return (n + 15) // 16 * 16 + 16
+
+
+class _Source:
+    """The CSV bytes: a device tensor and, when there is one, the host copy."""
+
+    def __init__(self, d_bytes, n: int, host: Optional[np.ndarray]):
+        self.d_bytes = d_bytes
+        self.n = n
+        self.host = host
+
+    def fetch(self, offset: int, length: int) -> bytes:
+        offset = max(0, offset)
+        end = min(self.n, offset + length)
+        if end <= offset:
+            return b""
+        if self.host is not None:
+            return self.host[offset:end].tobytes()
+        return self.d_bytes[offset:end].cpu().numpy().tobytes()
+
+    def take_lines(self, offset: int, k: int) -> Tuple[bytes, int]:
+        """Bytes of the first k physical lines starting at `offset` (fewer at EOF)."""
+        window = 1 << 16
+        while True:
+            chunk = self.fetch(offset, window)
+            ends = []
+            for m in _TERMINATOR.finditer(chunk):
+                # a '\r' at the very end of the window may be half of a '\r\n'
+                if m.end() == len(chunk) and chunk[-1:] == b"\r" and offset + len(chunk) < self.n:
+                    break
+                ends.append(m.end())
+                if len(ends) == k:
+                    return chunk[: ends[-1]], k
+            if offset + len(chunk) >= self.n:
+                tail = chunk[ends[-1]:] if ends else chunk
+                return chunk, len(ends) + (1 if tail else 0)
+            window *= 4
+
+    def count_terminators_before(self, pos: int) -> int:
+        """csv row index of the row containing byte `pos` (error path only)."""
+        torch = _torch()
+        total = 0
+        step = 1 << 28
+        for a in range(0, pos, step):
+            b = min(pos, a + step)
+            seg = self.d_bytes[a:b]
+            nxt = self.d_bytes[a + 1 : b + 1]
+            lf = seg == 10
+            cr = seg == 13
+            total += int(lf.sum().item()) + int((cr & (nxt != 10)).sum().item())
+        return total
+
+
+class ViconLoader:
+    """Reusable loader bound to one CUDA device and stream."""
+
+    def __init__(self, device=None, stream=None):
+        torch = _torch()
+        self.torch = torch
+        self.device = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        self.stream = stream
+        self.lib = nat.lib()
+        self._pinned = None
+        self._pinned_summary = torch.empty(ctypes.sizeof(nat.ScanSummary) + 8, dtype=torch.uint8, pin_memory=True)
+
+    # ---- public -----------------------------------------------------------------------------
+    def load_file(self, csv_filename) -> ViconNexusData:
+        torch = self.torch
+        size = os.path.getsize(csv_filename)  # FileNotFoundError propagates unwrapped, like open()
+        staging = self._staging(size)
+        view = staging.numpy()
+        with open(csv_filename, "rb") as fh:
+            got = fh.readinto(memoryview(view)[:size])
+        if got != size:
+            raise IOError(f"short read on {csv_filename}: {got} of {size} bytes")
+        return self._load_host(view[:size], staging, str(csv_filename))
+
+    def load_bytes(self, data, name: str = "<bytes>") -> ViconNexusData:
+        """`data`: bytes / bytearray / uint8 numpy array / uint8 CPU tensor holding the CSV."""
+        torch = self.torch
+        if isinstance(data, torch.Tensor):
+            if data.is_cuda:
+                return self.load_device(data, name=name)
+            host = data.numpy()
+        else:
+            host = np.frombuffer(data, dtype=np.uint8) if not isinstance(data, np.ndarray) else data
+        n = host.shape[0]
+        if isinstance(data, torch.Tensor) and data.is_pinned():
+            staging = data
+        else:
+            staging = self._staging(n)
+            staging.numpy()[:n] = host
+        return self._load_host(host, staging, name)
+
+    def load_device(self, d_bytes, n: Optional[int] = None, name: str = "<device bytes>", host=None) -> ViconNexusData:
+        """CSV bytes already in HBM.  The tensor must be readable 16 bytes past `n` rounded up
+        to 16 (allocate it with `padded_size(n)`)."""
+        n = int(d_bytes.numel() if n is None else n)
+        if d_bytes.numel() < _pad16(n):
+            torch = self.torch
+            padded = torch.empty(_pad16(n), dtype=torch.uint8, device=self.device)
+            padded[:n].copy_(d_bytes[:n])
+            d_bytes = padded
+        return self._run(_Source(d_bytes, n, host), name)
+
+    @staticmethod
+    def padded_size(n: int) -> int:
+        return _pad16(n)
+
+    # ---- internals -----------------------------------------------------------------------------
+    def _staging(self, n: int):
+        torch = self.torch
+        need = _pad16(n)
+        if self._pinned is None or self._pinned.numel() < need:
+            self._pinned = torch.empty(max(need, 1 << 20), dtype=torch.uint8, pin_memory=True)
+        return self._pinned
+
+    def _stream_ptr(self):
+        s = self.stream if self.stream is not None else self.torch.cuda.current_stream(self.device)
+        return s, ctypes.c_void_p(s.cuda_stream)
+
+    def _load_host(self, host: np.ndarray, staging, name: str) -> ViconNexusData:
+        torch = self.torch
+        n = int(host.shape[0])
+        stream, _ = self._stream_ptr()
+        with torch.cuda.stream(stream):
+            d_bytes = torch.empty(_pad16(n), dtype=torch.uint8, device=self.device)
+            if n:
+                d_bytes[:n].copy_(staging[:n], non_blocking=True)
+        return self._run(_Source(d_bytes, n, host), name)
+
+    def _scan(self, src: _Source):
+        torch = self.torch
+        stream, sptr = self._stream_ptr()
+        ws_bytes = int(self.lib.ms_workspace_bytes(src.n))
+        with torch.cuda.stream(stream):
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            d_summary = torch.empty(ctypes.sizeof(nat.ScanSummary), dtype=torch.uint8, device=self.device)
+            nat.check(
+                self.lib.ms_scan(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary.data_ptr(), sptr),
+                "ms_scan",
+            )
+            self._pinned_summary[: d_summary.numel()].copy_(d_summary, non_blocking=True)
+        stream.synchronize()
+        summary = nat.ScanSummary.from_buffer_copy(self._pinned_summary.numpy()[: d_summary.numel()].tobytes())
+        return summary, ws
+
+    def _run(self, src: _Source, name: str) -> ViconNexusData:
+        torch = self.torch
+        summary, ws = self._scan(src)
+        plan = _plan(src, summary, name)
+        stream, sptr = self._stream_ptr()
+
+        sections = (nat.Section * nat.MS_MAX_SECTIONS)()
+        blocks: List[Optional[SectionBlock]] = []
+        n_sec = 0
+        with torch.cuda.stream(stream):
+            for lay, (r0, r1) in zip(plan.layouts, plan.data_rows):
+                if lay is None or not lay.complete:
+                    blocks.append(None)
+                    continue
+                n_rows = max(0, r1 - r0)
+                block = torch.empty((lay.n_keep, n_rows), dtype=torch.float64, device=self.device)
+                blocks.append(SectionBlock(block, n_rows))
+                if n_rows > 0:
+                    s = sections[n_sec]
+                    s.row_begin, s.row_end = r0, r1
+                    s.num_cols, s.n_keep = lay.num_cols, lay.n_keep
+                    s.d_out = block.data_ptr() if lay.n_keep > 0 else None
+                    s.stride = n_rows
+                    n_sec += 1
+            d_status = torch.empty(1, dtype=torch.int64, device=self.device)
+            nat.check(
+                self.lib.ms_parse(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), sections, n_sec, d_status.data_ptr(), sptr),
+                "ms_parse",
+            )
+            h_status = self._pinned_summary[-8:].view(torch.int64)
+            h_status.copy_(d_status, non_blocking=True)
+        stream.synchronize()
+        key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
+        if key != nat.MS_ERR_NONE:
+            _raise_device_error(src, plan, key, name)
+        if plan.deferred_error is not None:
+            raise plan.deferred_error
+        return _build(plan, blocks)
+
+
+# ---- planning: which rows are what ------------------------------------------------------------------
+class _Plan:
+    def __init__(self):
+        self.layouts: List[Optional[SectionLayout]] = [None, None]
+        self.data_rows: List[Tuple[int, int]] = [(0, 0), (0, 0)]
+        self.deferred_error: Optional[Exception] = None  # raised if the data rows before it are clean
+
+
+def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, machine: HeaderMachine, name: str):
+    """Feeds up to five header rows starting at csv row `first_row` / byte `offset`.
+    Returns (error or None, header_bytes)."""
+    want = min(_HEADER_LINES, max(0, n_rows_total - first_row))
+    if want == 0:
+        return None, b""
+    chunk, n_lines = src.take_lines(offset, want)
+    rows, consumed = rows_from_bytes(chunk, want)
+    if consumed != len(rows) or len(rows) != min(want, n_lines):
+        raise NotImplementedError(
+            f"{name}: a quoted field spans several lines in the header of row {first_row + 1}; "
+            "not supported by the CUDA loader"
+        )
+    for i, row in enumerate(rows):
+        try:
+            machine.feed(row)
+        except Exception as exc:  # noqa: BLE001 - the reference wraps everything (load_csv.py:131)
+            return wrap_error(first_row + i + 1, name, exc), chunk
+    return None, chunk
+
+
+def _plan(src: _Source, summary, name: str) -> _Plan:
+    plan = _Plan()
+    n_rows = int(summary.n_rows)
+    if summary.flags & nat.MS_SCAN_BLANK_OVERFLOW:
+        raise NotImplementedError(f"{name}: more blank rows than the CUDA loader can order ({summary.n_blank_rows})")
+    blanks = [(int(summary.blank_row[i]), int(summary.blank_end[i])) for i in range(int(summary.n_reported))]
+    all_reported = int(summary.n_reported) == int(summary.n_blank_rows)
+
+    def first_blank_from(row: int):
+        for b in blanks:
+            if b[0] >= row:
+                return b
+        if not all_reported:
+            raise NotImplementedError(f"{name}: too many blank rows before the section separator")
+        return None
+
+    if summary.flags & nat.MS_SCAN_HAS_HIGH_BYTES and src.host is not None:
+        # open(filename) decodes the whole file; undecodable bytes raise before any parsing
+        # of the chunk they are in (UnicodeDecodeError, never wrapped: load_csv.py:128)
+        src.host.tobytes().decode(file_encoding())
+
+    # ---- section 1 header
+    m1 = HeaderMachine(SectionType.FORCES_EMG)
+    err, hdr1 = _feed_header(src, 0, 0, n_rows, m1, name)
+    header_quotes = hdr1.count(b'"')
+    if err is not None:
+        raise err  # lines 1-5: nothing can precede it
+    plan.layouts[0] = m1.layout
+    if not m1.done:
+        return plan  # file ends inside the first header
+    _check_supported(m1.layout, name)
+    b1 = first_blank_from(_HEADER_LINES)
+    end1 = b1[0] if b1 is not None else n_rows
+    plan.data_rows[0] = (_HEADER_LINES, end1)
+    if b1 is None:
+        _check_quotes(summary, header_quotes, name)
+        return plan
+
+    # ---- section 2 header
+    m2 = HeaderMachine(SectionType.TRAJECTORIES)
+    err, hdr2 = _feed_header(src, b1[1] + 1, b1[0] + 1, n_rows, m2, name)
+    header_quotes += hdr2.count(b'"')
+    _check_quotes(summary, header_quotes, name)
+    if err is not None:
+        plan.deferred_error = err
+        return plan
+    plan.layouts[1] = m2.layout
+    if not m2.done:
+        return plan
+    _check_supported(m2.layout, name)
+    first2 = b1[0] + 1 + _HEADER_LINES
+    b2 = first_blank_from(first2)
+    end2 = b2[0] if b2 is not None else n_rows
+    plan.data_rows[1] = (first2, end2)
+
+    # ---- anything after the second blank row is an error in the reference (Appendix C)
+    if b2 is not None and b2[0] + 1 < n_rows:
+        m3 = HeaderMachine(None)
+        err, _ = _feed_header(src, b2[1] + 1, b2[0] + 1, min(n_rows, b2[0] + 2), m3, name)
+        if err is None:  # pragma: no cover - every row raises in this state
+            raise AssertionError("row after the second blank row did not raise")
+        plan.deferred_error = err
+    return plan
+
+
+def _check_supported(lay: SectionLayout, name: str):
+    if lay.num_cols < 3:
+        raise NotImplementedError(f"{name}: a section header with fewer than 3 columns is not supported")
+
+
+def _check_quotes(summary, header_quotes: int, name: str):
+    if int(summary.n_quotes) > header_quotes:
+        raise NotImplementedError(f"{name}: quoted fields in data rows are not supported by the CUDA loader yet")
+
+
+def _raise_device_error(src: _Source, plan: _Plan, key: int, name: str):
+    pos, kind = key >> 3, key & 7
+    if kind == nat.MS_ERR_KIND_ROW_TOO_LONG:
+        raise NotImplementedError(
+            f"{name}: a CSV row longer than {nat.MS_MAX_ROW_BYTES} bytes near byte {pos} is not supported"
+        )
+    row_index = src.count_terminators_before(pos)
+    # the row: from the terminator before `pos` to the one after it
+    lo = max(0, pos - nat.MS_MAX_ROW_BYTES - 2)
+    window = src.fetch(lo, 2 * nat.MS_MAX_ROW_BYTES + 4)
+    rel = pos - lo
+    start = 0
+    for m in _TERMINATOR.finditer(window, 0, rel):
+        start = m.end()
+    m = _TERMINATOR.search(window, start)
+    line_bytes = window[start : m.end()] if m else window[start:]
+    rows, _ = rows_from_bytes(line_bytes, 1)
+    num_cols = 0
+    for lay, (r0, r1) in zip(plan.layouts, plan.data_rows):
+        if lay is not None and r0 <= row_index < r1:
+            num_cols = lay.num_cols
+    try:
+        replay_data_row(rows[0] if rows else [], num_cols)
+    except Exception as exc:  # noqa: BLE001
+        raise wrap_error(row_index + 1, name, exc) from exc
+    if kind == nat.MS_ERR_KIND_NON_ASCII:
+        raise NotImplementedError(
+            f"{name}: line {row_index + 1} has a non-ASCII numeric field; CPython accepts it but the CUDA loader does not"
+        )
+    raise AssertionError(f"{name}: device rejected a field on line {row_index + 1} that float() accepts")
+
+
+def _build(plan: _Plan, blocks) -> ViconNexusData:
+    """Builder.build (user_data.py:310-433)."""
+    lay1, lay2 = plan.layouts
+    freq1 = lay1.frequency if lay1 is not None else None
+    freq2 = lay2.frequency if lay2 is not None else None
+    num_frames = max(0, plan.data_rows[1][1] - plan.data_rows[1][0])
+    sampling = SamplingFreq(freq1, freq2, num_frames)
+    trackers = (ForcesEMGFrameTracker(sampling), TrajFrameTracker(sampling))
+    by_type = {}
+    for lay, block, tracker in zip((lay1, lay2), blocks, trackers):
+        if lay is None:
+            continue
+        if lay.devices and not lay.complete:
+            # the file ended before the units line: DeviceData(units=None) -> tuple(None)
+            # (user_data.py:710)
+            raise TypeError("'NoneType' object is not iterable")
+        for dev in lay.devices:
+            data = DeviceData(
+                dev.name, dev.device_type, dev.units, tracker, None,
+                block=block, first_channel=dev.first_col - 2, coords=dev.coords,
+            )
+            by_type.setdefault(dev.device_type, []).append(data)
+    emgs = by_type.get(DeviceType.EMG, [])
+    if len(emgs) != 1:
+        raise ValueError(f"found {len(emgs)} EMG devices - expected one")
+    for needed in (DeviceType.FORCE_PLATE, DeviceType.TRAJECTORY_MARKER):
+        if needed not in by_type:
+            raise KeyError(needed)
+    return ViconNexusData(
+        forcepl=by_type[DeviceType.FORCE_PLATE], emg=emgs[0], traj=by_type[DeviceType.TRAJECTORY_MARKER]
+    )
+
+
+# ---- module-level convenience ---------------------------------------------------------------------------
+_default_loaders = {}
+
+
+def _default_loader() -> ViconLoader:
+    torch = _torch()
+    dev = torch.cuda.current_device()
+    if dev not in _default_loaders:
+        _default_loaders[dev] = ViconLoader(f"cuda:{dev}")
+    return _default_loaders[dev]
+
+
+def load_vicon_file(csv_filename) -> ViconNexusData:
+    """Load data from a Vicon Nexus CSV file (drop-in for load_csv.py:96-135)."""
+    return _default_loader().load_file(csv_filename)
+
+
+def load_vicon_bytes(data, name: str = "<bytes>") -> ViconNexusData:
+    """Same as load_vicon_file for CSV bytes already in memory (host or CUDA uint8)."""
+    return _default_loader().load_bytes(data, name)

@@ -1,0 +1,67 @@
+"""The C-ABI library builds for sm_100a, loads without a GPU and exports every symbol
+include/ms_b200.h declares (no compute calls here)."""
+import ctypes
+import os
+import re
+import subprocess
+
+from conftest import ROOT
+
+
+def _declared_functions():
+    text = open(os.path.join(ROOT, "include", "ms_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    names = re.findall(r"\b(ms_[a-z0-9_]+)\s*\(", text)
+    return sorted(set(names))
+
+
+def test_header_declares_the_path():
+    names = _declared_functions()
+    for needed in ("ms_scan", "ms_parse", "ms_find_transitions", "ms_cut_windows", "ms_workspace_bytes"):
+        assert needed in names
+
+
+def test_library_builds_and_exports_every_declared_symbol():
+    import __graft_entry__ as g
+
+    g.build()
+    from muscle_synergies_b200 import _native
+
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    for name in _declared_functions():
+        assert hasattr(lib, name), f"{name} declared in include/ms_b200.h but not exported"
+    assert b"sm_100a" in _native.lib().ms_version()
+    assert _native.lib().ms_workspace_bytes(1 << 20) > 0
+
+
+def test_library_contains_sm_100a_code():
+    from muscle_synergies_b200 import _native
+
+    out = subprocess.run(["cuobjdump", "-lelf", _native.LIB_PATH], capture_output=True, text=True)
+    if out.returncode != 0:  # cuobjdump missing: not a failure of the build
+        return
+    assert "sm_100a" in out.stdout
+
+
+def test_no_cpu_fallback_without_gpu():
+    import pytest
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    import muscle_synergies_b200 as ms
+    from muscle_synergies_b200._native import NativeError
+
+    with pytest.raises(NativeError):
+        ms.load_vicon_file(os.path.join(ROOT, "tests", "golden", "abridged_data.csv"))
+
+
+def test_product_does_not_import_oracle():
+    pkg = os.path.join(ROOT, "muscle_synergies_b200")
+    for base, _dirs, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(base, f), errors="ignore").read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" or \
+                    "import oracle" not in text and "from oracle" not in text, f
+                assert "import oracle" not in text and "from oracle" not in text, f
