@@ -15,6 +15,7 @@
 #include "ms_parse_double.cuh"
 
 // ---- workspace layout ------------------------------------------------------------------------
+#define MS_TILE_BLANK_SLOTS 8
 struct MsTileInfo {
     uint32_t n_term;      // terminator ends inside the tile
     uint32_t flags;       // MS_TI_*
@@ -22,8 +23,10 @@ struct MsTileInfo {
     int32_t last_term;    // tile-relative offset of the last terminator end, -1 if none
     uint32_t n_quotes;
     uint32_t n_blank;     // blank rows fully decided inside the tile
-    int32_t blank_pos[2]; // tile-relative terminator-end offsets of the first two of them
+    int32_t blank_pos[MS_TILE_BLANK_SLOTS];  // tile-relative terminator-end offsets of the first of them, ascending
+    int32_t pad[2];
 };
+static_assert(sizeof(MsTileInfo) == 64, "MsTileInfo layout");
 #define MS_TI_HAS_TERM 1u
 #define MS_TI_NB_TAIL 2u    // non-blank byte after the last terminator (or anywhere if none)
 #define MS_TI_NB_HEAD 4u    // non-blank byte before the first terminator
@@ -31,7 +34,7 @@ struct MsTileInfo {
 #define MS_TI_OVERFLOW 16u  // more than MS_TILE_BLANK_CAP blank rows in the tile
 #define MS_TI_HAS_CR 32u
 
-#define MS_TILE_BLANK_CAP 16
+#define MS_TILE_BLANK_CAP 16  // >= MS_TILE_BLANK_SLOTS
 
 static inline int64_t ms_num_tiles(int64_t n) { return (n + MS_TILE_BYTES - 1) / MS_TILE_BYTES; }
 
@@ -249,20 +252,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __
             f |= MS_TI_OVERFLOW;
             nbk = MS_TILE_BLANK_CAP;
         }
-        // two smallest positions, ascending
-        int a = 0x7fffffff, b = 0x7fffffff;
-        for (int i = 0; i < nbk; i++) {
-            int p = s_blank[i];
-            if (p < a) {
-                b = a;
-                a = p;
-            } else if (p < b) {
-                b = p;
+        // smallest positions first (insertion sort of at most MS_TILE_BLANK_CAP entries)
+        for (int i = 1; i < nbk; i++) {
+            int x = s_blank[i], j = i - 1;
+            while (j >= 0 && s_blank[j] > x) {
+                s_blank[j + 1] = s_blank[j];
+                j--;
             }
+            s_blank[j + 1] = x;
         }
         ti.n_blank = (uint32_t)s_blank_count;
-        ti.blank_pos[0] = a == 0x7fffffff ? -1 : a;
-        ti.blank_pos[1] = b == 0x7fffffff ? -1 : b;
+        for (int i = 0; i < MS_TILE_BLANK_SLOTS; i++) ti.blank_pos[i] = i < nbk ? s_blank[i] : -1;
+        ti.pad[0] = ti.pad[1] = 0;
         ti.flags = f;
         tiles[tile] = ti;
     }
@@ -348,7 +349,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
         if (ti.flags & MS_TI_HAS_CR) my_flags |= MS_SCAN_HAS_CR;
         const int64_t t0 = k * (int64_t)MS_TILE_BYTES;
         my_blank += ti.n_blank;
-        for (int i = 0; i < 2; i++) {
+        for (int i = 0; i < MS_TILE_BLANK_SLOTS; i++) {
             if (ti.blank_pos[i] >= 0) {
                 int slot = atomicAdd(&s_ncand, 1);
                 if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.blank_pos[i];
@@ -370,7 +371,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
             }
         }
     }
-    // tiles with more than two decided blank rows: their 3rd.. positions are not recorded;
+    // tiles with more than MS_TILE_BLANK_SLOTS decided blank rows: the rest is not recorded;
     // harmless unless they are among the first MS_MAX_BLANK_ROWS of the file (flagged below)
     if (my_quotes) atomicAdd(&s_quotes, my_quotes);
     if (my_blank) atomicAdd(&s_blank_total, my_blank);
@@ -420,13 +421,13 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
             }
             s_cand[j + 1] = x;
         }
-        // a tile that decided more than two blank rows only recorded two: if one of the
+        // a tile that decided more than MS_TILE_BLANK_SLOTS blank rows did not record all: if one of the
         // first MS_MAX_BLANK_ROWS candidates comes from such a tile the order is unreliable
         int nrep = nc < MS_MAX_BLANK_ROWS ? nc : MS_MAX_BLANK_ROWS;
         for (int i = 0; i < nrep; i++) {
             long long p = s_cand[i];
             int64_t k = p >= n ? n_tiles - 1 : p / MS_TILE_BYTES;
-            if (tiles[k].n_blank > 2) s_flags |= MS_SCAN_BLANK_OVERFLOW;
+            if (tiles[k].n_blank > MS_TILE_BLANK_SLOTS) s_flags |= MS_SCAN_BLANK_OVERFLOW;
         }
         s_nrep = nrep;
     }
