@@ -4,8 +4,9 @@
 //   ms_resolve_kernel  single CTA: terminator prefix per tile, blank rows that straddle
 //                      tiles, their csv row indices -> ms_scan_summary
 //   ms_parse_kernel    pass 2, one CTA per tile: (row, column) of every field by a block-wide
-//                      segmented scan over delimiter masks, correctly rounded decimal->double
-//                      per field, scatter into channel-major float64 arrays
+//                      segmented scan over delimiter masks -> shared (row x column) table of
+//                      field offsets -> column-major sweep: correctly rounded decimal->double,
+//                      coalesced stores into channel-major float64 arrays
 //
 // Replaces the per-row Python of the reference (reader.py:886-948, aggregator.py:96-124,
 // 229-241, user_data.py:391-396); see include/ms_b200.h for the boundary.
@@ -469,6 +470,20 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 // ===================================================================================================
 // pass 2
 // ===================================================================================================
+// One CTA per 64 KiB tile; the CTA owns the rows that START inside the tile and reads up to
+// MS_MAX_ROW_BYTES past it to finish the last one.
+//
+//   1. stage the bytes in shared memory (16-byte coalesced loads)
+//   2. per thread: comma / terminator bit masks of a contiguous 144-byte chunk (registers)
+//   3. block-wide segmented scan -> (row, column, start of the field in progress) at every chunk
+//   4. walk: every delimiter of a data row writes "field c+1 starts here" into a shared
+//      (row x column) table of byte offsets
+//   5. parse: warps sweep the table COLUMN-major - the 32 lanes of a warp parse the same column of
+//      32 consecutive rows (similar text in every lane, little divergence) and store 32
+//      consecutive doubles of one channel (coalesced 256-byte stores, no transpose staging)
+//
+// Steps 4-5 run once per (section, batch of rows); a batch is as many rows as fit the table, so
+// pathological inputs (thousands of tiny rows in a tile) only cost more rounds.
 #define PARSE_THREADS 512
 #define PARSE_WARPS (PARSE_THREADS / 32)
 #define PARSE_REGION (MS_TILE_BYTES + MS_MAX_ROW_BYTES)  // bytes staged per CTA
@@ -476,7 +491,13 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 #define PARSE_SEGS (PARSE_CHUNK / 16)
 static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGION, "chunking");
 #define PARSE_PAD 16  // bytes staged before and after the region
-#define PARSE_SMEM (PARSE_REGION + 2 * PARSE_PAD)
+#define PARSE_BYTES_SMEM (PARSE_REGION + 2 * PARSE_PAD)
+#define PARSE_TAB_ENTRIES 10240  // uint32 field-start table
+#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_TAB_ENTRIES * 4)
+#define TAB_NONE 0xFFFFFFFFu
+#define TAB_CRLF 0x80000000u    // on an end entry: the terminator was "\r\n", the field ends one byte earlier
+#define TAB_ROWEND 0x40000000u  // the delimiter was a row terminator: no further field in this row
+#define TAB_OFFSET 0x3FFFFFFFu
 
 struct MsSectionsArg {
     ms_section s[MS_MAX_SECTIONS];
@@ -484,8 +505,8 @@ struct MsSectionsArg {
 };
 
 struct MsScanElem {
-    int n_term;    // terminators in the span
-    int c_tail;    // commas after the last terminator of the span (all commas if none)
+    int n_term;      // terminators in the span
+    int c_tail;      // commas after the last terminator of the span (all commas if none)
     int has_term;
     int last_delim;  // region offset of the last delimiter (comma / terminator) in the span, -1 if none
 };
@@ -510,7 +531,8 @@ struct MsParsed {
     uint64_t bits;
     int status;
 };
-// One out-of-line copy of the field parser: the walk below is unrolled per 16-byte segment.
+// General (exact for every input) parser, out of line: the fast path below handles what Vicon
+// exports actually contain.
 __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uint8_t* e) {
     MsParsed r;
     r.bits = MS_NAN_BITS;
@@ -518,30 +540,62 @@ __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uin
     return r;
 }
 
-struct MsRowCtx {  // where the fields of the current row go
-    double* out;   // &d_out[row - row_begin], NULL when the row is not a data row of this CTA
-    int64_t stride;
-    int num_cols, n_keep;
-};
-
-__device__ __forceinline__ MsRowCtx ms_row_ctx(const MsSectionsArg& secs, long long row, bool owned) {
-    MsRowCtx c;
-    c.out = nullptr;
-    c.stride = 0;
-    c.num_cols = 0;
-    c.n_keep = 0;
-    if (owned) {
-#pragma unroll
-        for (int i = 0; i < MS_MAX_SECTIONS; i++) {
-            if (i < secs.n && row >= secs.s[i].row_begin && row < secs.s[i].row_end) {
-                c.out = secs.s[i].d_out + (row - secs.s[i].row_begin);
-                c.stride = secs.s[i].stride;
-                c.num_cols = secs.s[i].num_cols;
-                c.n_keep = secs.s[i].n_keep;
-            }
+// [-]digits[.digits][(e|E)[+-]digits] with at most 9 significant digits and a decimal exponent
+// within Clinger's exact range: one IEEE multiply or divide.  Returns false when the text is
+// anything else (the caller then takes the general parser, which also produces the errors).
+__device__ __forceinline__ bool ms_parse_fast(const uint8_t* p, const uint8_t* e, uint64_t* bits) {
+    uint64_t sign = 0;
+    if (*p == '-') {
+        sign = 0x8000000000000000ull;
+        p++;
+    }
+    uint32_t acc = 0;
+    int nsig = 0, nfrac = 0, ndig = 0;
+    bool dot = false;
+    unsigned c = 0;
+    for (; p < e; p++) {
+        c = *p;
+        const unsigned d = c - '0';
+        if (d <= 9u) {
+            ndig++;
+            nsig += (acc | d) != 0;
+            acc = acc * 10u + d;
+            nfrac += dot;
+        } else if (c == '.' && !dot) {
+            dot = true;
+        } else {
+            break;
         }
     }
-    return c;
+    if (ndig == 0 || nsig > 9) return false;
+    int q = -nfrac;
+    if (p < e) {
+        if ((c | 0x20u) != 'e') return false;
+        p++;
+        if (p >= e) return false;
+        bool eneg = false;
+        if (*p == '-' || *p == '+') {
+            eneg = *p == '-';
+            p++;
+        }
+        if (p >= e || e - p > 3) return false;
+        int ex = 0;
+        for (; p < e; p++) {
+            const unsigned d = (unsigned)*p - '0';
+            if (d > 9u) return false;
+            ex = ex * 10 + (int)d;
+        }
+        q += eneg ? -ex : ex;
+    }
+    if (acc == 0) {
+        *bits = sign;
+        return true;
+    }
+    if (q < -22 || q > 22) return false;
+    double v = (double)acc;
+    v = q < 0 ? v / ms_pow10_double[-q] : v * ms_pow10_double[q];
+    *bits = sign | ms_double_to_bits(v);
+    return true;
 }
 
 __global__ void __launch_bounds__(PARSE_THREADS)
@@ -549,6 +603,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
                     const MsSectionsArg secs, unsigned long long* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
+    uint32_t* const tab = reinterpret_cast<uint32_t*>(smem_raw + PARSE_BYTES_SMEM);
     __shared__ MsScanElem s_warp[PARSE_WARPS];
     __shared__ int s_lt_end, s_total_terms;
 
@@ -558,14 +613,14 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     const int tile_len = (int)min((int64_t)MS_TILE_BYTES, n - t0);
 
     // rows of this tile that can be data rows at all?  (cheap early exit for header-only tiles)
-    const unsigned long long row_lo = term_prefix[tile], row_hi = term_prefix[tile + 1] + 1;
+    const long long row_lo = (long long)term_prefix[tile], row_hi = (long long)term_prefix[tile + 1] + 1;
     bool any = false;
     for (int i = 0; i < secs.n; i++)
-        if ((long long)row_hi >= secs.s[i].row_begin && (long long)row_lo < secs.s[i].row_end) any = true;
+        if (row_hi >= secs.s[i].row_begin && row_lo < secs.s[i].row_end) any = true;
     if (!any) return;
 
-    // ---- stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
-    for (int i = tid; i < PARSE_SMEM / 16; i += PARSE_THREADS) {
+    // ---- 1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
+    for (int i = tid; i < PARSE_BYTES_SMEM / 16; i += PARSE_THREADS) {
         int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
         uint4 v;
         if (off < 0)
@@ -576,7 +631,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     }
     __syncthreads();
 
-    // ---- delimiter masks of my chunk, kept in registers
+    // ---- 2. delimiter masks of my chunk, kept in registers
     const int c0 = tid * PARSE_CHUNK;
     uint32_t mterm[PARSE_SEGS], mcomma[PARSE_SEGS];
     MsScanElem mine;
@@ -622,7 +677,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
         }
     }
 
-    // ---- block-wide exclusive scan
+    // ---- 3. block-wide exclusive scan
     MsScanElem inc = mine;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
@@ -638,7 +693,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     before.last_delim = -1;
     for (int w = 0; w < warp; w++) before = ms_elem_combine(before, s_warp[w]);
     MsScanElem prev_lane = ms_elem_shfl_up(inc, 1);
-    MsScanElem excl = lane == 0 ? before : ms_elem_combine(before, prev_lane);
+    const MsScanElem excl = lane == 0 ? before : ms_elem_combine(before, prev_lane);
     if (lt_end_part >= 0) s_lt_end = excl.n_term + lt_end_part;
     if (tid == PARSE_THREADS - 1) s_total_terms = excl.n_term + mine.n_term;
     __syncthreads();
@@ -648,71 +703,111 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
     const int lt_first = starts_at_t0 ? 0 : 1;
     const int lt_last = s_lt_end;  // inclusive
-    if (lt_last >= lt_first && s_total_terms < lt_last + 1) {
+    if (lt_last < lt_first) return;
+    if (s_total_terms < lt_last + 1) {
         // the last owned row does not end inside the staged region
         if (tid == 0) atomicMin(status, ((unsigned long long)t0 << 3) | MS_ERR_KIND_ROW_TOO_LONG);
         return;
     }
 
-    // ---- walk my chunk: every delimiter ends a field
-    int lt = excl.n_term;
-    int col = excl.c_tail;
-    int fs = excl.last_delim + 1;  // start of the field in progress
-    bool owned = lt >= lt_first && lt <= lt_last;
-    MsRowCtx ctx = ms_row_ctx(secs, (long long)row_lo + lt, owned);
-    if (lt > lt_last) return;  // whole chunk belongs to the next tile
-
-#pragma unroll
-    for (int s = 0; s < PARSE_SEGS; s++) {
-        const int p0 = c0 + s * 16;
-        uint32_t term = mterm[s], comma = mcomma[s];
-        uint32_t dl = term | comma;
-        if (!dl) continue;
-        if (!term && (ctx.out == nullptr || col >= ctx.num_cols)) {
-            // nothing to parse here: only commas of a row we skip or of its ignored tail
-            col += __popc(comma);
-            fs = p0 + 32 - __clz(dl);
-            continue;
+    for (int si = 0; si < secs.n; si++) {
+        // local rows of this section owned by this tile
+        const long long a_ll = max((long long)lt_first, secs.s[si].row_begin - row_lo);
+        const long long b_ll = min((long long)lt_last, secs.s[si].row_end - 1 - row_lo);
+        if (a_ll > b_ll) continue;
+        const int sec_a = (int)a_ll, sec_b = (int)b_ll;
+        const int ncols = secs.s[si].num_cols;
+        const int n_keep = secs.s[si].n_keep;
+        const int tstride = (ncols + 1) | 1;  // odd: lanes of a warp read different banks
+        const int rows_per_batch = PARSE_TAB_ENTRIES / tstride;
+        if (rows_per_batch < 1) {
+            if (tid == 0) atomicMin(status, ((unsigned long long)t0 << 3) | MS_ERR_KIND_ROW_TOO_LONG);
+            return;
         }
-        while (dl) {
-            const int b = __ffs(dl) - 1;
-            dl &= dl - 1u;
-            const int p = p0 + b;
-            const bool is_term = (term >> b) & 1u;
-            if (ctx.out != nullptr && col < ctx.num_cols) {
-                int fe = p;
-                if (is_term && fe > fs && reg[fe - 1] == '\r') fe--;
+        double* const out_base = secs.s[si].d_out;
+        const int64_t out_stride = secs.s[si].stride;
+        const long long out_row0 = row_lo - secs.s[si].row_begin;  // output row of local row 0
+
+        for (int ba = sec_a; ba <= sec_b; ba += rows_per_batch) {
+            const int bb = min(sec_b, ba + rows_per_batch - 1);
+            const int nrows = bb - ba + 1;
+            // ---- 4a. clear the table
+            for (int i = tid; i < nrows * tstride; i += PARSE_THREADS) tab[i] = TAB_NONE;
+            __syncthreads();
+            // ---- 4b. walk my chunk: every delimiter ends a field and starts the next
+            {
+                int lt = excl.n_term;
+                int col = excl.c_tail;
+                int fs = excl.last_delim + 1;  // start of the field in progress
+                if (tid == 0 && starts_at_t0 && ba == 0) tab[0] = 0u;  // row 0 starts at the first byte
+#pragma unroll
+                for (int s = 0; s < PARSE_SEGS; s++) {
+                    const int p0 = c0 + s * 16;
+                    const uint32_t term = mterm[s], comma = mcomma[s];
+                    uint32_t dl = term | comma;
+                    if (!dl || lt > bb) continue;
+                    if (!term && (lt < ba || col >= ncols)) {
+                        // only commas of a row outside the batch, or of the ignored tail of a row
+                        col += __popc(comma);
+                        fs = p0 + 32 - __clz(dl);
+                        continue;
+                    }
+                    while (dl) {
+                        const int b = __ffs(dl) - 1;
+                        dl &= dl - 1u;
+                        const int p = p0 + b;
+                        const bool is_term = (term >> b) & 1u;
+                        if (lt >= ba && lt <= bb && col < ncols) {
+                            uint32_t v = (uint32_t)(p + 1);
+                            if (is_term) {
+                                v |= TAB_ROWEND;
+                                if (p > fs && reg[p - 1] == '\r') v |= TAB_CRLF;
+                            }
+                            tab[(lt - ba) * tstride + col + 1] = v;
+                        }
+                        if (is_term) {
+                            lt++;
+                            col = 0;
+                            if (lt >= ba && lt <= bb) tab[(lt - ba) * tstride] = (uint32_t)(p + 1);
+                        } else {
+                            col++;
+                        }
+                        fs = p + 1;
+                    }
+                }
+            }
+            __syncthreads();
+            // ---- 5. parse, column-major over the table
+            const int groups = (nrows + 31) >> 5;
+            const int items = groups * ncols;
+            for (int item = warp; item < items; item += PARSE_WARPS) {
+                const int g = item / ncols, c = item - g * ncols;
+                const int r = (g << 5) + lane;
+                if (r >= nrows) continue;
+                const uint32_t sv = tab[r * tstride + c];
                 uint64_t bits = MS_NAN_BITS;
-                if (fe > fs) {
-                    MsParsed pr = ms_parse_field_call(reg + fs, reg + fe);
-                    bits = pr.bits;
-                    if (pr.status != MS_PARSE_OK) {
-                        bits = MS_NAN_BITS;
-                        atomicMin(status,
-                                  ((unsigned long long)(t0 + fs) << 3) |
-                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+                if (sv != TAB_NONE && !(sv & TAB_ROWEND)) {  // the row has a field c
+                    const uint32_t ev = tab[r * tstride + c + 1];
+                    const int fs = (int)(sv & TAB_OFFSET);
+                    const int fe = (int)(ev & TAB_OFFSET) - 1 - (int)(ev >> 31);
+                    if (fe > fs) {
+                        if (!ms_parse_fast(reg + fs, reg + fe, &bits)) {
+                            MsParsed pr = ms_parse_field_call(reg + fs, reg + fe);
+                            bits = pr.bits;
+                            if (pr.status != MS_PARSE_OK) {
+                                bits = MS_NAN_BITS;
+                                atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
+                                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII
+                                                                                      : MS_ERR_KIND_BAD_FLOAT));
+                            }
+                        }
                     }
                 }
-                const int ch = col - 2;
-                if (ch >= 0 && ch < ctx.n_keep) ctx.out[(int64_t)ch * ctx.stride] = ms_bits_to_double(bits);
+                const int ch = c - 2;
+                if (ch >= 0 && ch < n_keep)
+                    out_base[(int64_t)ch * out_stride + (out_row0 + ba + r)] = ms_bits_to_double(bits);
             }
-            if (is_term) {
-                // short row: the cells it does not have are NaN (pandas pads ragged rows)
-                if (ctx.out != nullptr) {
-                    for (int c = max(col + 1, 2); c < ctx.num_cols; c++) {
-                        const int ch = c - 2;
-                        if (ch < ctx.n_keep) ctx.out[(int64_t)ch * ctx.stride] = ms_bits_to_double(MS_NAN_BITS);
-                    }
-                }
-                lt++;
-                col = 0;
-                if (lt > lt_last) return;
-                owned = lt >= lt_first;
-                ctx = ms_row_ctx(secs, (long long)row_lo + lt, owned);
-            } else {
-                col++;
-            }
-            fs = p + 1;
+            __syncthreads();  // the table is reused by the next batch
         }
     }
 }
