@@ -473,17 +473,20 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 // One CTA per 64 KiB tile; the CTA owns the rows that START inside the tile and reads up to
 // MS_MAX_ROW_BYTES past it to finish the last one.
 //
-//   1. stage the bytes in shared memory (16-byte coalesced loads)
-//   2. per thread: comma / terminator bit masks of a contiguous 144-byte chunk (registers)
-//   3. block-wide segmented scan -> (row, column, start of the field in progress) at every chunk
-//   4. walk: every delimiter of a data row writes "field c+1 starts here" into a shared
-//      (row x column) table of byte offsets
-//   5. parse: warps sweep the table COLUMN-major - the 32 lanes of a warp parse the same column of
-//      32 consecutive rows (similar text in every lane, little divergence) and store 32
-//      consecutive doubles of one channel (coalesced 256-byte stores, no transpose staging)
+//   A. stage the bytes in shared memory (16-byte coalesced loads); per thread, comma and
+//      terminator bit masks of a contiguous 144-byte chunk; block-wide prefix sum of the
+//      terminator counts -> start offset of every owned row (shared array); comma masks are kept
+//      in shared memory for step B's column lookups
+//   B. one LANE per row, lanes in lockstep over the columns: the 32 lanes of a warp parse the
+//      same column of 32 consecutive rows (same kind of text in every lane -> little
+//      divergence), walking their row left to right and finding each field's end while parsing
+//      it, and store 32 consecutive doubles of one channel (coalesced 256-byte stores, no
+//      transpose staging).  The ignored tail of a row (fields beyond num_cols) is never touched.
+//      To keep all warps busy a row group is split into column chunks; a chunk locates its first
+//      column with a popcount walk over the row's comma masks.
 //
-// Steps 4-5 run once per (section, batch of rows); a batch is as many rows as fit the table, so
-// pathological inputs (thousands of tiny rows in a tile) only cost more rounds.
+// Rows are processed in batches of PARSE_ROWS_CAP per section, so pathological inputs
+// (thousands of tiny rows in a tile) only cost more rounds.
 #define PARSE_THREADS 512
 #define PARSE_WARPS (PARSE_THREADS / 32)
 #define PARSE_REGION (MS_TILE_BYTES + MS_MAX_ROW_BYTES)  // bytes staged per CTA
@@ -492,46 +495,20 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGION, "chunking");
 #define PARSE_PAD 16  // bytes staged before and after the region
 #define PARSE_BYTES_SMEM (PARSE_REGION + 2 * PARSE_PAD)
-#define PARSE_TAB_ENTRIES 10240  // uint32 field-start table
-#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_TAB_ENTRIES * 4)
-#define TAB_NONE 0xFFFFFFFFu
-#define TAB_CRLF 0x80000000u    // on an end entry: the terminator was "\r\n", the field ends one byte earlier
-#define TAB_ROWEND 0x40000000u  // the delimiter was a row terminator: no further field in this row
-#define TAB_OFFSET 0x3FFFFFFFu
+#define PARSE_NSEG (PARSE_REGION / 16)
+#define PARSE_ROWS_CAP 1024
+#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
 
 struct MsSectionsArg {
     ms_section s[MS_MAX_SECTIONS];
     int n;
 };
 
-struct MsScanElem {
-    int n_term;      // terminators in the span
-    int c_tail;      // commas after the last terminator of the span (all commas if none)
-    int has_term;
-    int last_delim;  // region offset of the last delimiter (comma / terminator) in the span, -1 if none
-};
-__device__ __forceinline__ MsScanElem ms_elem_combine(MsScanElem a, MsScanElem b) {
-    MsScanElem r;
-    r.n_term = a.n_term + b.n_term;
-    r.c_tail = b.has_term ? b.c_tail : a.c_tail + b.c_tail;
-    r.has_term = a.has_term | b.has_term;
-    r.last_delim = max(a.last_delim, b.last_delim);
-    return r;
-}
-__device__ __forceinline__ MsScanElem ms_elem_shfl_up(MsScanElem e, int d) {
-    MsScanElem r;
-    r.n_term = __shfl_up_sync(0xffffffffu, e.n_term, d);
-    r.c_tail = __shfl_up_sync(0xffffffffu, e.c_tail, d);
-    r.has_term = __shfl_up_sync(0xffffffffu, e.has_term, d);
-    r.last_delim = __shfl_up_sync(0xffffffffu, e.last_delim, d);
-    return r;
-}
-
 struct MsParsed {
     uint64_t bits;
     int status;
 };
-// General (exact for every input) parser, out of line: the fast path below handles what Vicon
+// General (exact for every input) parser, out of line: the inline path below handles what Vicon
 // exports actually contain.
 __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uint8_t* e) {
     MsParsed r;
@@ -540,72 +517,101 @@ __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uin
     return r;
 }
 
-// [-]digits[.digits][(e|E)[+-]digits] with at most 9 significant digits and a decimal exponent
-// within Clinger's exact range: one IEEE multiply or divide.  Returns false when the text is
-// anything else (the caller then takes the general parser, which also produces the errors).
-__device__ __forceinline__ bool ms_parse_fast(const uint8_t* p, const uint8_t* e, uint64_t* bits) {
-    uint64_t sign = 0;
-    if (*p == '-') {
-        sign = 0x8000000000000000ull;
-        p++;
-    }
-    uint32_t acc = 0;
-    int nsig = 0, nfrac = 0, ndig = 0;
-    bool dot = false;
-    unsigned c = 0;
-    for (; p < e; p++) {
-        c = *p;
-        const unsigned d = c - '0';
-        if (d <= 9u) {
-            ndig++;
-            nsig += (acc | d) != 0;
-            acc = acc * 10u + d;
-            nfrac += dot;
-        } else if (c == '.' && !dot) {
-            dot = true;
+__device__ __forceinline__ bool ms_is_delim(unsigned c) { return c == ',' || c == '\n' || c == '\r'; }
+
+// Parses the field that starts at *pp and advances *pp past its delimiter.
+//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] with <= 9 significant digits and a decimal
+//                exponent in Clinger's exact range -> one IEEE multiply or divide;
+//   anything else: the field's extent is found and the general parser decides (and reports errors).
+// Returns true when the delimiter ended the row.
+__device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, int* pp, uint64_t* bits_out,
+                                              unsigned long long* status, int64_t t0) {
+    const int fs = *pp;
+    const uint8_t* q = reg + fs;
+    unsigned c = *q;
+    uint64_t bits = MS_NAN_BITS;
+    if (!ms_is_delim(c)) {
+        uint64_t sign = 0;
+        if (c == '-') {
+            sign = 0x8000000000000000ull;
+            c = *++q;
+        }
+        uint32_t acc = 0;
+        int nsig = 0, nfrac = 0, ndig = 0;
+        bool dot = false;
+        for (;;) {
+            const unsigned d = c - '0';
+            if (d <= 9u) {
+                ndig++;
+                nsig += (acc | d) != 0;
+                acc = acc * 10u + d;
+                nfrac += dot;
+            } else if (c == '.' && !dot) {
+                dot = true;
+            } else {
+                break;
+            }
+            c = *++q;
+        }
+        int ex = -nfrac;
+        bool ok = ndig > 0 && nsig <= 9;
+        if (ok && (c | 0x20u) == 'e') {
+            // exponent: at most three digits
+            const uint8_t* r = q + 1;
+            unsigned cc = *r;
+            bool eneg = false;
+            if (cc == '-' || cc == '+') {
+                eneg = cc == '-';
+                cc = *++r;
+            }
+            int ev = 0, nd = 0;
+            while (cc - '0' <= 9u && nd < 4) {
+                ev = ev * 10 + (int)(cc - '0');
+                nd++;
+                cc = *++r;
+            }
+            if (nd >= 1 && nd <= 3 && ms_is_delim(cc)) {
+                ex += eneg ? -ev : ev;
+                q = r;
+                c = cc;
+            } else {
+                ok = false;
+            }
+        }
+        if (ok && ms_is_delim(c) && (acc == 0 || (ex >= -22 && ex <= 22))) {
+            if (acc == 0) {
+                bits = sign;
+            } else {
+                double v = (double)acc;
+                v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
+                bits = sign | ms_double_to_bits(v);
+            }
         } else {
-            break;
+            // general path: [fs, fe) up to the next delimiter
+            while (!ms_is_delim(c)) c = *++q;
+            MsParsed pr = ms_parse_field_call(reg + fs, q);
+            bits = pr.bits;
+            if (pr.status != MS_PARSE_OK) {
+                bits = MS_NAN_BITS;
+                atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
+                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+            }
         }
     }
-    if (ndig == 0 || nsig > 9) return false;
-    int q = -nfrac;
-    if (p < e) {
-        if ((c | 0x20u) != 'e') return false;
-        p++;
-        if (p >= e) return false;
-        bool eneg = false;
-        if (*p == '-' || *p == '+') {
-            eneg = *p == '-';
-            p++;
-        }
-        if (p >= e || e - p > 3) return false;
-        int ex = 0;
-        for (; p < e; p++) {
-            const unsigned d = (unsigned)*p - '0';
-            if (d > 9u) return false;
-            ex = ex * 10 + (int)d;
-        }
-        q += eneg ? -ex : ex;
-    }
-    if (acc == 0) {
-        *bits = sign;
-        return true;
-    }
-    if (q < -22 || q > 22) return false;
-    double v = (double)acc;
-    v = q < 0 ? v / ms_pow10_double[-q] : v * ms_pow10_double[q];
-    *bits = sign | ms_double_to_bits(v);
-    return true;
+    *bits_out = bits;
+    *pp = (int)(q - reg) + 1;
+    return c != ',';
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS)
+__global__ void __launch_bounds__(PARSE_THREADS, 2)
     ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
                     const MsSectionsArg secs, unsigned long long* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
-    uint32_t* const tab = reinterpret_cast<uint32_t*>(smem_raw + PARSE_BYTES_SMEM);
-    __shared__ MsScanElem s_warp[PARSE_WARPS];
-    __shared__ int s_lt_end, s_total_terms;
+    uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
+    int* const row_start = reinterpret_cast<int*>(smem_raw + PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32);
+    __shared__ int s_warp_terms[PARSE_WARPS];
+    __shared__ int s_lt_end;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
@@ -619,7 +625,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
         if (row_hi >= secs.s[i].row_begin && row_lo < secs.s[i].row_end) any = true;
     if (!any) return;
 
-    // ---- 1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
+    // ---- A1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
     for (int i = tid; i < PARSE_BYTES_SMEM / 16; i += PARSE_THREADS) {
         int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
         uint4 v;
@@ -631,14 +637,10 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     }
     __syncthreads();
 
-    // ---- 2. delimiter masks of my chunk, kept in registers
+    // ---- A2. delimiter masks of my chunk
     const int c0 = tid * PARSE_CHUNK;
-    uint32_t mterm[PARSE_SEGS], mcomma[PARSE_SEGS];
-    MsScanElem mine;
-    mine.n_term = 0;
-    mine.c_tail = 0;
-    mine.has_term = 0;
-    mine.last_delim = -1;
+    uint32_t mterm[PARSE_SEGS];
+    int my_terms = 0;
     int lt_end_part = -1;  // terminators of my chunk before position tile_len - 1, if it is mine
 #pragma unroll
     for (int s = 0; s < PARSE_SEGS; s++) {
@@ -648,19 +650,9 @@ __global__ void __launch_bounds__(PARSE_THREADS)
         uint32_t next_lf = reg[p0 + 16] == '\n';
         uint32_t term = ms_term16(d.lf, d.cr, next_lf);
         mterm[s] = term;
-        mcomma[s] = d.comma;
-        if (term) {
-            int hi = 31 - __clz(term);
-            mine.c_tail = __popc(d.comma >> (hi + 1));
-            mine.has_term = 1;
-        } else {
-            mine.c_tail += __popc(d.comma);
-        }
-        mine.n_term += __popc(term);
-        uint32_t dl = term | d.comma;
-        if (dl) mine.last_delim = p0 + 31 - __clz(dl);
+        cmask[tid * PARSE_SEGS + s] = (uint16_t)d.comma;
+        my_terms += __popc(term);
     }
-    // terminators strictly before region offset tile_len - 1 decide which rows start inside the tile
     {
         const int q = tile_len - 1;
         if (q >= c0 && q < c0 + PARSE_CHUNK) {
@@ -676,26 +668,23 @@ __global__ void __launch_bounds__(PARSE_THREADS)
             lt_end_part = cnt;
         }
     }
-
-    // ---- 3. block-wide exclusive scan
-    MsScanElem inc = mine;
+    // ---- A3. block-wide exclusive prefix sum of terminator counts
+    int inc = my_terms;
 #pragma unroll
     for (int d = 1; d < 32; d <<= 1) {
-        MsScanElem o = ms_elem_shfl_up(inc, d);
-        if (lane >= d) inc = ms_elem_combine(o, inc);
+        int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
     }
-    if (lane == 31) s_warp[warp] = inc;
+    if (lane == 31) s_warp_terms[warp] = inc;
     __syncthreads();
-    MsScanElem before;  // everything before my warp
-    before.n_term = 0;
-    before.c_tail = 0;
-    before.has_term = 0;
-    before.last_delim = -1;
-    for (int w = 0; w < warp; w++) before = ms_elem_combine(before, s_warp[w]);
-    MsScanElem prev_lane = ms_elem_shfl_up(inc, 1);
-    const MsScanElem excl = lane == 0 ? before : ms_elem_combine(before, prev_lane);
-    if (lt_end_part >= 0) s_lt_end = excl.n_term + lt_end_part;
-    if (tid == PARSE_THREADS - 1) s_total_terms = excl.n_term + mine.n_term;
+    int before = 0, total_terms = 0;
+    for (int w = 0; w < PARSE_WARPS; w++) {
+        const int v = s_warp_terms[w];
+        if (w < warp) before += v;
+        total_terms += v;
+    }
+    const int lt0 = before + inc - my_terms;  // terminators before my chunk
+    if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
     __syncthreads();
 
     // ---- ownership: rows that START in [t0, t0 + tile_len)
@@ -704,7 +693,7 @@ __global__ void __launch_bounds__(PARSE_THREADS)
     const int lt_first = starts_at_t0 ? 0 : 1;
     const int lt_last = s_lt_end;  // inclusive
     if (lt_last < lt_first) return;
-    if (s_total_terms < lt_last + 1) {
+    if (total_terms < lt_last + 1) {
         // the last owned row does not end inside the staged region
         if (tid == 0) atomicMin(status, ((unsigned long long)t0 << 3) | MS_ERR_KIND_ROW_TOO_LONG);
         return;
@@ -718,96 +707,74 @@ __global__ void __launch_bounds__(PARSE_THREADS)
         const int sec_a = (int)a_ll, sec_b = (int)b_ll;
         const int ncols = secs.s[si].num_cols;
         const int n_keep = secs.s[si].n_keep;
-        const int tstride = (ncols + 1) | 1;  // odd: lanes of a warp read different banks
-        const int rows_per_batch = PARSE_TAB_ENTRIES / tstride;
-        if (rows_per_batch < 1) {
-            if (tid == 0) atomicMin(status, ((unsigned long long)t0 << 3) | MS_ERR_KIND_ROW_TOO_LONG);
-            return;
-        }
         double* const out_base = secs.s[si].d_out;
         const int64_t out_stride = secs.s[si].stride;
         const long long out_row0 = row_lo - secs.s[si].row_begin;  // output row of local row 0
 
-        for (int ba = sec_a; ba <= sec_b; ba += rows_per_batch) {
-            const int bb = min(sec_b, ba + rows_per_batch - 1);
+        for (int ba = sec_a; ba <= sec_b; ba += PARSE_ROWS_CAP) {
+            const int bb = min(sec_b, ba + PARSE_ROWS_CAP - 1);
             const int nrows = bb - ba + 1;
-            // ---- 4a. clear the table
-            for (int i = tid; i < nrows * tstride; i += PARSE_THREADS) tab[i] = TAB_NONE;
-            __syncthreads();
-            // ---- 4b. walk my chunk: every delimiter ends a field and starts the next
+            // ---- A4. start offset of rows ba .. bb+1 (the last one closes row bb)
+            if (tid == 0 && starts_at_t0 && ba == 0) row_start[0] = 0;
             {
-                int lt = excl.n_term;
-                int col = excl.c_tail;
-                int fs = excl.last_delim + 1;  // start of the field in progress
-                if (tid == 0 && starts_at_t0 && ba == 0) tab[0] = 0u;  // row 0 starts at the first byte
+                int lt = lt0;
 #pragma unroll
                 for (int s = 0; s < PARSE_SEGS; s++) {
-                    const int p0 = c0 + s * 16;
-                    const uint32_t term = mterm[s], comma = mcomma[s];
-                    uint32_t dl = term | comma;
-                    if (!dl || lt > bb) continue;
-                    if (!term && (lt < ba || col >= ncols)) {
-                        // only commas of a row outside the batch, or of the ignored tail of a row
-                        col += __popc(comma);
-                        fs = p0 + 32 - __clz(dl);
-                        continue;
-                    }
-                    while (dl) {
-                        const int b = __ffs(dl) - 1;
-                        dl &= dl - 1u;
-                        const int p = p0 + b;
-                        const bool is_term = (term >> b) & 1u;
-                        if (lt >= ba && lt <= bb && col < ncols) {
-                            uint32_t v = (uint32_t)(p + 1);
-                            if (is_term) {
-                                v |= TAB_ROWEND;
-                                if (p > fs && reg[p - 1] == '\r') v |= TAB_CRLF;
-                            }
-                            tab[(lt - ba) * tstride + col + 1] = v;
-                        }
-                        if (is_term) {
-                            lt++;
-                            col = 0;
-                            if (lt >= ba && lt <= bb) tab[(lt - ba) * tstride] = (uint32_t)(p + 1);
-                        } else {
-                            col++;
-                        }
-                        fs = p + 1;
+                    uint32_t term = mterm[s];
+                    while (term) {
+                        const int b = __ffs(term) - 1;
+                        term &= term - 1u;
+                        lt++;  // the row that starts after this terminator
+                        if (lt >= ba && lt <= bb + 1) row_start[lt - ba] = c0 + s * 16 + b + 1;
                     }
                 }
             }
             __syncthreads();
-            // ---- 5. parse, column-major over the table
+
+            // ---- B. lanes = rows, lockstep over columns
             const int groups = (nrows + 31) >> 5;
-            const int items = groups * ncols;
+            int nchunks = (2 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 2 items per warp
+            nchunks = max(1, min(nchunks, ncols / 4));
+            const int cs = (ncols + nchunks - 1) / nchunks;  // columns per chunk
+            nchunks = (ncols + cs - 1) / cs;
+            const int items = groups * nchunks;
             for (int item = warp; item < items; item += PARSE_WARPS) {
-                const int g = item / ncols, c = item - g * ncols;
+                const int g = item / nchunks, k = item - g * nchunks;
                 const int r = (g << 5) + lane;
                 if (r >= nrows) continue;
-                const uint32_t sv = tab[r * tstride + c];
-                uint64_t bits = MS_NAN_BITS;
-                if (sv != TAB_NONE && !(sv & TAB_ROWEND)) {  // the row has a field c
-                    const uint32_t ev = tab[r * tstride + c + 1];
-                    const int fs = (int)(sv & TAB_OFFSET);
-                    const int fe = (int)(ev & TAB_OFFSET) - 1 - (int)(ev >> 31);
-                    if (fe > fs) {
-                        if (!ms_parse_fast(reg + fs, reg + fe, &bits)) {
-                            MsParsed pr = ms_parse_field_call(reg + fs, reg + fe);
-                            bits = pr.bits;
-                            if (pr.status != MS_PARSE_OK) {
-                                bits = MS_NAN_BITS;
-                                atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
-                                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII
-                                                                                      : MS_ERR_KIND_BAD_FLOAT));
-                            }
-                        }
+                const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
+                int p = row_start[r];
+                bool done = false;
+                if (c_lo > 0) {
+                    // first byte of column c_lo = one past the c_lo-th comma of the row, if the row has it
+                    const int row_end = row_start[r + 1];  // one past the row's terminator
+                    int seg = p >> 4;
+                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
+                    int need = c_lo;
+                    int cnt = __popc(m);
+                    while (cnt < need && (seg << 4) < row_end) {
+                        need -= cnt;
+                        m = cmask[++seg];
+                        cnt = __popc(m);
+                    }
+                    if (cnt < need) {
+                        done = true;
+                    } else {
+                        for (int i = 1; i < need; i++) m &= m - 1u;
+                        p = (seg << 4) + __ffs(m);  // position after that comma
+                        // the comma must belong to this row (a terminator may come first)
+                        if (p > row_end - 1) done = true;
                     }
                 }
-                const int ch = c - 2;
-                if (ch >= 0 && ch < n_keep)
-                    out_base[(int64_t)ch * out_stride + (out_row0 + ba + r)] = ms_bits_to_double(bits);
+                double* out = out_base + (int64_t)(c_lo - 2) * out_stride + (out_row0 + ba + r);
+                for (int c = c_lo; c < c_hi; c++, out += out_stride) {
+                    uint64_t bits = MS_NAN_BITS;
+                    if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
+                    const int ch = c - 2;
+                    if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                }
             }
-            __syncthreads();  // the table is reused by the next batch
+            __syncthreads();  // row_start is reused by the next batch
         }
     }
 }
