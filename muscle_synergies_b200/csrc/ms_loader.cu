@@ -42,6 +42,7 @@ static inline int64_t ms_num_tiles(int64_t n) { return (n + MS_TILE_BYTES - 1) /
 struct MsWorkspaceView {
     MsTileInfo* tiles;
     unsigned long long* term_prefix;  // terminator ends before the tile
+    uint32_t* masks;                  // per 16-byte segment: terminator-end bits | comma bits << 16
 };
 
 __host__ __device__ static inline int64_t ms_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
@@ -49,13 +50,17 @@ __host__ __device__ static inline int64_t ms_align_up(int64_t x, int64_t a) { re
 static MsWorkspaceView ms_view(void* ws, int64_t n_tiles) {
     MsWorkspaceView v;
     v.tiles = (MsTileInfo*)ws;
-    v.term_prefix = (unsigned long long*)((char*)ws + ms_align_up(n_tiles * (int64_t)sizeof(MsTileInfo), 256));
+    char* p = (char*)ws + ms_align_up(n_tiles * (int64_t)sizeof(MsTileInfo), 256);
+    v.term_prefix = (unsigned long long*)p;
+    p += ms_align_up((n_tiles + 1) * 8, 256);
+    v.masks = (uint32_t*)p;
     return v;
 }
 
 extern "C" int64_t ms_workspace_bytes(int64_t n_bytes) {
     int64_t t = ms_num_tiles(n_bytes < 1 ? 1 : n_bytes);
-    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256);
+    int64_t segs = (n_bytes < 1 ? 1 : n_bytes + 15) / 16 + 8;
+    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256) + ms_align_up(segs * 4, 256);
 }
 
 // ---- shared helpers --------------------------------------------------------------------------------
@@ -86,6 +91,8 @@ __device__ __forceinline__ uint4 ms_load16(const uint8_t* __restrict__ src, int6
 // ===================================================================================================
 #define SCAN_THREADS 256
 #define SCAN_WARPS (SCAN_THREADS / 32)
+#define SCAN_SPAN (MS_TILE_BYTES / SCAN_WARPS)  // bytes of the tile one warp walks
+#define SCAN_ITERS (SCAN_SPAN / 512)
 
 struct MsRun {  // state of the row in progress
     uint32_t has_term;  // a terminator was seen (in the span this state summarises)
@@ -98,157 +105,190 @@ __device__ __forceinline__ MsRun ms_run_combine(MsRun a, MsRun b) {
     return r;
 }
 
+struct MsWarpSummary {
+    uint32_t n_term, n_quotes, flags;
+    uint32_t has_term, nb_tail, nb_head;  // nb_head: non-blank before the span's first terminator
+    int first_term, last_term;            // tile-relative, -1 if none
+};
+
+// Each warp walks a contiguous 8 KiB span of the tile, 512 bytes (one coalesced 16-byte load per
+// lane) per iteration, carrying the state of the row in progress in registers; the eight warp
+// summaries are combined once at the end.  The delimiter masks are written out so that pass 2
+// does not classify the bytes again.
 __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __restrict__ src, int64_t n,
-                                                                MsTileInfo* __restrict__ tiles) {
+                                                                MsTileInfo* __restrict__ tiles,
+                                                                uint32_t* __restrict__ masks) {
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
     const int64_t t0 = tile * (int64_t)MS_TILE_BYTES;
 
-    __shared__ MsRun s_warp_run[2][SCAN_WARPS];
+    __shared__ MsWarpSummary s_warp[SCAN_WARPS];
     __shared__ int s_blank_count;
     __shared__ int s_blank[MS_TILE_BLANK_CAP];
-    __shared__ int s_first_term, s_last_term;
-    __shared__ uint32_t s_nb_head;
-    __shared__ uint32_t s_nterm, s_nquote, s_flags;
-
-    if (tid == 0) {
-        s_blank_count = 0;
-        s_first_term = -1;
-        s_last_term = -1;
-        s_nb_head = 0;
-        s_nterm = 0;
-        s_nquote = 0;
-        s_flags = 0;
-    }
+    if (tid == 0) s_blank_count = 0;
     __syncthreads();
 
-    MsRun run;  // block-uniform: state at the start of the current iteration
+    MsRun run;  // warp-uniform: state at the start of the current iteration
     run.has_term = 0;
     run.nb_tail = 0;
     uint32_t my_nterm = 0, my_nquote = 0, my_flags = 0;
+    int w_first = -1, w_last = -1;  // meaningful in the lane that sees them; reduced at the end
+    uint32_t w_nb_head = 0;
 
-    const int iters = MS_TILE_BYTES / (SCAN_THREADS * 16);
-    for (int it = 0; it < iters; it++) {
-        const int rel = (it * SCAN_THREADS + tid) * 16;
+    for (int it = 0; it < SCAN_ITERS; it++) {
+        const int rel = warp * SCAN_SPAN + it * 512 + lane * 16;
         const int64_t off = t0 + rel;
+        if (t0 + warp * SCAN_SPAN + it * 512 >= n) break;  // warp-uniform: nothing left in this span
         // beyond the end: commas (blank, not a terminator)
-        uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
-        MsDelims d = ms_delims16(v);
-        uint32_t quote = ms_mask16(ms_eq_flags(v.x, 0x22222222u), ms_eq_flags(v.y, 0x22222222u),
-                                   ms_eq_flags(v.z, 0x22222222u), ms_eq_flags(v.w, 0x22222222u));
-        uint32_t ws = ms_mask16(ms_strip_space_flags(v.x), ms_strip_space_flags(v.y), ms_strip_space_flags(v.z),
-                                ms_strip_space_flags(v.w));
-        uint32_t nb = ~(ws | d.comma) & 0xffffu;
-        if ((v.x | v.y | v.z | v.w) & 0x80808080u) my_flags |= MS_TI_HIGH;
-        if (d.cr) my_flags |= MS_TI_HAS_CR;
+        const uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        uint32_t lf16 = 0, cr16 = 0, comma16 = 0, gt16 = 0, hib = 0;
+#pragma unroll
+        for (int k = 0; k < 4; k++) {
+            lf16 |= ms_gather4(ms_eq_flags(w[k], 0x0a0a0a0au)) << (4 * k);
+            cr16 |= ms_gather4(ms_eq_flags(w[k], 0x0d0d0d0du)) << (4 * k);
+            comma16 |= ms_gather4(ms_eq_flags(w[k], 0x2c2c2c2cu)) << (4 * k);
+            gt16 |= ms_gather4(ms_ge_flags(w[k], 0x21212121u)) << (4 * k);
+            my_nquote += __popc(ms_eq_flags(w[k], 0x22222222u));
+            hib |= w[k];
+        }
+        if (hib & 0x80808080u) my_flags |= MS_TI_HIGH;
+        if (cr16) my_flags |= MS_TI_HAS_CR;
+        uint32_t nb = gt16 & ~comma16;
+        if (~gt16 & ~lf16 & ~cr16 & 0xffffu) {
+            // rare: spaces, tabs or control bytes - the exact str.strip() whitespace set decides
+            const uint32_t ws = ms_mask16(ms_strip_space_flags(v.x), ms_strip_space_flags(v.y),
+                                          ms_strip_space_flags(v.z), ms_strip_space_flags(v.w));
+            nb = ~(ws | comma16) & 0xffffu;
+        }
         // byte after this vector: first byte of the next lane's vector
-        uint32_t next_lf = __shfl_down_sync(0xffffffffu, d.lf & 1u, 1);
+        uint32_t next_lf = __shfl_down_sync(0xffffffffu, lf16 & 1u, 1);
         if (lane == 31) next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
-        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
+        const uint32_t term = ms_term16(lf16, cr16, next_lf);
+        if (off < n) {
+            uint32_t cm = comma16;
+            if (off + 16 > n) cm &= (1u << (int)(n - off)) - 1u;  // not the fill bytes
+            masks[off >> 4] = term | (cm << 16);
+        }
         my_nterm += __popc(term);
-        my_nquote += __popc(quote);
 
         const uint32_t has_t = term != 0;
         uint32_t nb_head, nb_tail;
         if (has_t) {
-            uint32_t low = term & (0u - term);
+            const uint32_t low = term & (0u - term);
             nb_head = (nb & (low - 1u)) != 0;
-            int hi = 31 - __clz(term);
-            nb_tail = (nb >> (hi + 1)) != 0;
+            nb_tail = (nb >> (32 - __clz(term))) != 0;
         } else {
             nb_head = nb_tail = nb != 0;
         }
-
-        // ---- warp level: which non-blank state precedes each lane
         const uint32_t HT = __ballot_sync(0xffffffffu, has_t);
         const uint32_t NT = __ballot_sync(0xffffffffu, nb_tail);
         const uint32_t below = (1u << lane) - 1u;
-        // warp aggregate
-        if (lane == 0) {
-            MsRun w;
-            if (HT) {
-                int last = 31 - __clz(HT);
-                w.has_term = 1;
-                w.nb_tail = (NT >> last) != 0;  // tail of lane `last` and every lane after it
-            } else {
-                w.has_term = 0;
-                w.nb_tail = NT != 0;
-            }
-            s_warp_run[it & 1][warp] = w;
-        }
-        __syncthreads();
-        // state before this warp = run (previous iterations) + warps before it
-        MsRun before = run;
-        for (int w = 0; w < warp; w++) before = ms_run_combine(before, s_warp_run[it & 1][w]);
-        MsRun after = before;
-        for (int w = warp; w < SCAN_WARPS; w++) after = ms_run_combine(after, s_warp_run[it & 1][w]);
-
         if (has_t) {
-            // state just before this lane's vector
-            uint32_t ht = HT & below;
+            const uint32_t ht = HT & below;
             uint32_t carry, known;
             if (ht) {
-                int j = 31 - __clz(ht);
+                const int j = 31 - __clz(ht);
                 carry = ((NT & below) >> j) != 0;
                 known = 1;
             } else {
-                carry = before.nb_tail | ((NT & below) != 0);
-                known = before.has_term;
+                carry = run.nb_tail | ((NT & below) != 0);
+                known = run.has_term;
             }
             const int first_bit = __ffs(term) - 1;
-            const int pos = rel + first_bit;
             if (known) {
                 if (!(carry | nb_head)) {  // the row ending at my first terminator is blank
-                    int slot = atomicAdd(&s_blank_count, 1);
-                    if (slot < MS_TILE_BLANK_CAP) s_blank[slot] = pos;
+                    const int slot = atomicAdd(&s_blank_count, 1);
+                    if (slot < MS_TILE_BLANK_CAP) s_blank[slot] = rel + first_bit;
                 }
             } else {
-                // first terminator of the tile: its row began in an earlier tile
-                s_first_term = pos;
-                s_nb_head = carry | nb_head;
+                // first terminator of this warp's span: decided when the warps are combined
+                w_first = rel + first_bit;
+                w_nb_head = carry | nb_head;
             }
             // rows that begin and end inside this vector
             uint32_t rest = term & (term - 1u);
             int prev = first_bit;
             while (rest) {
-                int b = __ffs(rest) - 1;
+                const int b = __ffs(rest) - 1;
                 rest &= rest - 1u;
-                uint32_t between = (nb >> (prev + 1)) & ((1u << (b - prev - 1)) - 1u);
+                const uint32_t between = (nb >> (prev + 1)) & ((1u << (b - prev - 1)) - 1u);
                 if (!between) {
-                    int slot = atomicAdd(&s_blank_count, 1);
+                    const int slot = atomicAdd(&s_blank_count, 1);
                     if (slot < MS_TILE_BLANK_CAP) s_blank[slot] = rel + b;
                 }
                 prev = b;
             }
-            atomicMax(&s_last_term, rel + (31 - __clz(term)));
+            w_last = rel + 31 - __clz(term);
         }
-        run = after;
-        // s_warp_run[it & 1] is rewritten two iterations later, after another barrier
+        MsRun agg;
+        agg.has_term = HT != 0;
+        agg.nb_tail = HT ? ((NT >> (31 - __clz(HT))) != 0) : (NT != 0);
+        run = ms_run_combine(run, agg);
     }
 
-    // ---- tile totals
+    // ---- warp summary
+#pragma unroll
     for (int o = 16; o > 0; o >>= 1) {
-        my_nterm += __shfl_down_sync(0xffffffffu, my_nterm, o);
-        my_nquote += __shfl_down_sync(0xffffffffu, my_nquote, o);
-        my_flags |= __shfl_down_sync(0xffffffffu, my_flags, o);
+        my_nterm += __shfl_xor_sync(0xffffffffu, my_nterm, o);
+        my_nquote += __shfl_xor_sync(0xffffffffu, my_nquote, o);
+        my_flags |= __shfl_xor_sync(0xffffffffu, my_flags, o);
+        w_first = max(w_first, __shfl_xor_sync(0xffffffffu, w_first, o));  // set by exactly one lane
+        w_last = max(w_last, __shfl_xor_sync(0xffffffffu, w_last, o));
+        w_nb_head |= __shfl_xor_sync(0xffffffffu, w_nb_head, o);
     }
     if (lane == 0) {
-        atomicAdd(&s_nterm, my_nterm);
-        atomicAdd(&s_nquote, my_nquote);
-        atomicOr(&s_flags, my_flags);
+        MsWarpSummary ws;
+        ws.n_term = my_nterm;
+        ws.n_quotes = my_nquote;
+        ws.flags = my_flags;
+        ws.has_term = run.has_term;
+        ws.nb_tail = run.nb_tail;
+        ws.nb_head = run.has_term ? w_nb_head : run.nb_tail;
+        ws.first_term = w_first;
+        ws.last_term = w_last;
+        s_warp[warp] = ws;
     }
     __syncthreads();
+
     if (tid == 0) {
         MsTileInfo ti;
-        ti.n_term = s_nterm;
-        ti.n_quotes = s_nquote;
-        ti.first_term = s_first_term;
-        ti.last_term = s_last_term;
-        uint32_t f = s_flags;
-        if (run.has_term) f |= MS_TI_HAS_TERM;
-        if (run.nb_tail) f |= MS_TI_NB_TAIL;
-        if (s_nb_head) f |= MS_TI_NB_HEAD;
+        ti.n_term = 0;
+        ti.n_quotes = 0;
+        ti.first_term = -1;
+        ti.last_term = -1;
+        uint32_t f = 0, tile_nb_head = 0;
+        MsRun carry;
+        carry.has_term = 0;
+        carry.nb_tail = 0;
         int nbk = s_blank_count;
+        for (int w = 0; w < SCAN_WARPS; w++) {
+            const MsWarpSummary ws = s_warp[w];
+            ti.n_term += ws.n_term;
+            ti.n_quotes += ws.n_quotes;
+            f |= ws.flags;
+            if (ws.has_term) {
+                if (carry.has_term) {
+                    // the row ending at this span's first terminator began in an earlier span of the tile
+                    if (!(carry.nb_tail | ws.nb_head)) {
+                        if (nbk < MS_TILE_BLANK_CAP) s_blank[nbk] = ws.first_term;
+                        nbk++;
+                    }
+                } else {
+                    ti.first_term = ws.first_term;  // began in an earlier tile: ms_resolve_kernel decides
+                    tile_nb_head = carry.nb_tail | ws.nb_head;
+                }
+                ti.last_term = ws.last_term;
+            }
+            MsRun r;
+            r.has_term = ws.has_term;
+            r.nb_tail = ws.nb_tail;
+            carry = ms_run_combine(carry, r);
+        }
+        if (carry.has_term) f |= MS_TI_HAS_TERM;
+        if (carry.nb_tail) f |= MS_TI_NB_TAIL;
+        if (tile_nb_head) f |= MS_TI_NB_HEAD;
+        const int n_blank = nbk;
         if (nbk > MS_TILE_BLANK_CAP) {
             f |= MS_TI_OVERFLOW;
             nbk = MS_TILE_BLANK_CAP;
@@ -262,7 +302,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __
             }
             s_blank[j + 1] = x;
         }
-        ti.n_blank = (uint32_t)s_blank_count;
+        ti.n_blank = (uint32_t)n_blank;
         for (int i = 0; i < MS_TILE_BLANK_SLOTS; i++) ti.blank_pos[i] = i < nbk ? s_blank[i] : -1;
         ti.pad[0] = ti.pad[1] = 0;
         ti.flags = f;
@@ -605,7 +645,8 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
 
 __global__ void __launch_bounds__(PARSE_THREADS, 2)
     ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
-                    const MsSectionsArg secs, unsigned long long* __restrict__ status) {
+                    const uint32_t* __restrict__ masks, const MsSectionsArg secs,
+                    unsigned long long* __restrict__ status) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
     uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
     uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
@@ -637,21 +678,28 @@ __global__ void __launch_bounds__(PARSE_THREADS, 2)
     }
     __syncthreads();
 
-    // ---- A2. delimiter masks of my chunk
+    // ---- A2. delimiter masks of my chunk: classified once, by ms_scan_kernel
     const int c0 = tid * PARSE_CHUNK;
     uint32_t mterm[PARSE_SEGS];
     int my_terms = 0;
     int lt_end_part = -1;  // terminators of my chunk before position tile_len - 1, if it is mine
+    {
+        const int64_t n_seg = (n + 15) >> 4;
+        const int64_t seg0 = (t0 >> 4) + tid * PARSE_SEGS;
 #pragma unroll
-    for (int s = 0; s < PARSE_SEGS; s++) {
-        const int p0 = c0 + s * 16;
-        uint4 v = *reinterpret_cast<const uint4*>(reg + p0);
-        MsDelims d = ms_delims16(v);
-        uint32_t next_lf = reg[p0 + 16] == '\n';
-        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
-        mterm[s] = term;
-        cmask[tid * PARSE_SEGS + s] = (uint16_t)d.comma;
-        my_terms += __popc(term);
+        for (int s = 0; s < PARSE_SEGS; s++) {
+            const int64_t sa = seg0 + s;
+            uint32_t term = 0xffffu, comma = 0;  // beyond the end: every (fill) byte ends a row
+            if (sa < n_seg) {
+                const uint32_t mk = __ldg(masks + sa);
+                term = mk & 0xffffu;
+                comma = mk >> 16;
+                if (sa == n_seg - 1 && (n & 15)) term |= 0xffffu & ~((1u << (int)(n & 15)) - 1u);
+            }
+            mterm[s] = term;
+            cmask[tid * PARSE_SEGS + s] = (uint16_t)comma;
+            my_terms += __popc(term);
+        }
     }
     {
         const int q = tile_len - 1;
@@ -791,7 +839,7 @@ extern "C" int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspac
     const int64_t n_tiles = ms_num_tiles(n_bytes);
     MsWorkspaceView v = ms_view(d_workspace, ms_num_tiles(n_bytes < 1 ? 1 : n_bytes));
     if (n_tiles > 0) {
-        ms_scan_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles);
+        ms_scan_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks);
         MS_COUNT_LAUNCH();
         MS_CUDA_CHECK(cudaGetLastError());
     }
@@ -821,8 +869,8 @@ extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_w
     }
     if (n_tiles == 0 || arg.n == 0) return MS_OK;
     MS_CUDA_CHECK(cudaFuncSetAttribute(ms_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PARSE_SMEM));
-    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), n_tiles);
-    ms_parse_kernel<<<(unsigned)n_tiles, PARSE_THREADS, PARSE_SMEM, st>>>(d_bytes, n_bytes, v.term_prefix, arg,
+    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), ms_num_tiles(n_bytes < 1 ? 1 : n_bytes));
+    ms_parse_kernel<<<(unsigned)n_tiles, PARSE_THREADS, PARSE_SMEM, st>>>(d_bytes, n_bytes, v.term_prefix, v.masks, arg,
                                                                            (unsigned long long*)d_status);
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
