@@ -117,6 +117,22 @@ int ms_cut_windows(const double* d_src, int64_t src_stride, int32_t n_channels, 
                    const int64_t* d_stops, const int64_t* d_out_offsets, int32_t n_windows, double* d_out,
                    int64_t max_window_len, void* stream);
 
+/* ---- NMF by multiplicative updates (extension; not a reference-parity claim) --------------- */
+
+/* What analysis.py:862-863 asks scikit-learn for with solver="mu", beta_loss="frobenius":
+ *   W <- W * (X H^T) / (W (H H^T));  H <- H * (W^T X) / ((W^T W) H);  zero denominators -> float32 eps;
+ *   every check_every iterations (tol > 0) stop when (previous_error - error) / error_at_init < tol.
+ * One launch runs a whole batch of problems on the same X (rank sweep x restarts), fp32,
+ * X / W / H resident in shared memory.  d_X: [n][m] row-major (samples x muscles).
+ * h_ranks[p]: rank of problem p (1..16).  d_W / d_H: initial factors packed problem after
+ * problem (W_p [n][k_p], H_p [k_p][m], row-major); results overwrite them.  d_work:
+ * n_problems * 24 bytes.  Outputs per problem: d_n_iter, d_err = ||X - W H||_F,
+ * d_vaf [m + 1] = 1 - SS_res / SS_tot overall, then per column (analysis.py:642-667). */
+int32_t ms_nmf_resident_max_rows(int32_t m, int32_t kmax);
+int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_ranks, int32_t n_problems,
+                      float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every, void* d_work,
+                      int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------- */
 const char* ms_last_cuda_error(void);
 const char* ms_version(void);
