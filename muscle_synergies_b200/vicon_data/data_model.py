@@ -27,16 +27,39 @@ class SectionBlock:
         self.tensor = tensor  # torch.float64, (n_keep, stride) on the GPU, stride >= n_rows
         self.n_rows = n_rows
         self._host = None
+        self._pending = None  # (pinned tensor, event) of an asynchronous device->host copy
+
+    def prefetch_host(self, stream, pinned=None):
+        """Starts the device->host copy on `stream` (optionally into a caller-owned pinned
+        buffer of at least n_keep * n_rows doubles); `host()` waits for it."""
+        import torch
+
+        view = self.tensor[:, : self.n_rows]
+        if pinned is None:
+            dst = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
+        else:
+            dst = pinned[: view.numel()].view(view.shape)
+        with torch.cuda.stream(stream):
+            dst.copy_(view, non_blocking=True)
+            event = torch.cuda.Event()
+            event.record(stream)
+        self._pending = (dst, event)
 
     def host(self) -> np.ndarray:
         """(n_keep, n_rows) float64 numpy array (one device->host copy, cached)."""
         if self._host is None:
-            import torch
+            if self._pending is not None:
+                dst, event = self._pending
+                event.synchronize()
+                self._host = dst.numpy()
+                self._pending = None
+            else:
+                import torch
 
-            view = self.tensor[:, : self.n_rows]
-            pinned = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
-            pinned.copy_(view, non_blocking=False)
-            self._host = pinned.numpy()
+                view = self.tensor[:, : self.n_rows]
+                pinned = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
+                pinned.copy_(view, non_blocking=False)
+                self._host = pinned.numpy()
         return self._host
 
 

@@ -240,7 +240,67 @@ class ViconLoader:
             _raise_device_error(src, plan, key, name)
         if plan.deferred_error is not None:
             raise plan.deferred_error
-        return _build(plan, blocks)
+        data = _build(plan, blocks)
+        data.blocks = [b for b in blocks if b is not None]  # the per-section HBM blocks (extension)
+        return data
+
+    def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2):
+        """Pipelined batch load: yields one ViconNexusData per source, in order.
+
+        sources: pinned uint8 CPU tensors (or anything load_bytes accepts; non-pinned inputs
+        are staged through one pinned buffer and lose the overlap).  While file i is scanned
+        and parsed on the compute stream, file i+1 is copied host->device on a copy stream
+        and the arrays of file i-1 travel device->host on a third stream (PCIe is full
+        duplex).  With to_host the section blocks are copied into a ring of `host_slots`
+        pinned buffers: the host arrays of file i stay valid until file i + host_slots is
+        yielded.  Errors in a file are raised when that file is reached."""
+        torch = self.torch
+        sources = list(sources)
+        names = list(names) if names is not None else [f"<bytes {i}>" for i in range(len(sources))]
+        s_comp, _ = self._stream_ptr()
+        s_copy = torch.cuda.Stream(self.device)
+        s_d2h = torch.cuda.Stream(self.device)
+        ring = [dict() for _ in range(max(1, host_slots))]
+
+        def stage(i):
+            src = sources[i]
+            if isinstance(src, torch.Tensor) and not src.is_cuda and src.is_pinned():
+                pinned, n = src, int(src.numel())
+            else:
+                host = np.frombuffer(src, dtype=np.uint8) if not isinstance(src, (np.ndarray, torch.Tensor)) else src
+                host = host.numpy() if isinstance(host, torch.Tensor) else host
+                n = int(host.shape[0])
+                pinned = torch.empty(_pad16(n), dtype=torch.uint8, pin_memory=True)
+                pinned.numpy()[:n] = host
+            with torch.cuda.stream(s_copy):
+                d_bytes = torch.empty(_pad16(n), dtype=torch.uint8, device=self.device)
+                d_bytes[:n].copy_(pinned[:n], non_blocking=True)
+                ev = torch.cuda.Event()
+                ev.record(s_copy)
+            return d_bytes, n, ev, pinned
+
+        nxt = stage(0) if sources else None
+        for i in range(len(sources)):
+            d_bytes, n, ev, pinned = nxt
+            nxt = stage(i + 1) if i + 1 < len(sources) else None
+            s_comp.wait_event(ev)
+            d_bytes.record_stream(s_comp)
+            data = self._run(_Source(d_bytes, n, pinned.numpy()[:n]), names[i])
+            if to_host:
+                done = torch.cuda.Event()
+                done.record(s_comp)
+                s_d2h.wait_event(done)
+                slot = ring[i % len(ring)]
+                for bi, blk in enumerate(data.blocks):
+                    need = int(blk.tensor.shape[0]) * blk.n_rows
+                    buf = slot.get(bi)
+                    if buf is None or buf.numel() < need:
+                        buf = torch.empty(max(need, 1), dtype=torch.float64, pin_memory=True)
+                        slot[bi] = buf
+                    blk.tensor.record_stream(s_d2h)
+                    blk.prefetch_host(s_d2h, buf)
+            yield data
+        s_d2h.synchronize()
 
 
 # ---- planning: which rows are what ------------------------------------------------------------------
