@@ -559,45 +559,73 @@ __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uin
 
 __device__ __forceinline__ bool ms_is_delim(unsigned c) { return c == ',' || c == '\n' || c == '\r'; }
 
+// Four bytes at an arbitrary offset of the staged region (little endian): two aligned word
+// loads and a funnel shift.
+__device__ __forceinline__ uint32_t ms_load4(const uint8_t* __restrict__ reg, int p) {
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reg) + (p >> 2);
+    return __funnelshift_r(w[0], w[1], (p & 3) << 3);
+}
+
+// Value of four ASCII-digit bytes already reduced to 0..9 (first character most significant).
+__device__ __forceinline__ uint32_t ms_digits4(uint32_t t) {
+    const uint32_t v = (t * 10u + (t >> 8)) & 0x00ff00ffu;  // two-digit values in bytes 0 and 2
+    return (v & 0xffu) * 100u + (v >> 16);
+}
+
 // Parses the field that starts at *pp and advances *pp past its delimiter.
-//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] with <= 9 significant digits and a decimal
-//                exponent in Clinger's exact range -> one IEEE multiply or divide;
+//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] with <= 19 digits, mantissa <= 2^53 and a
+//                decimal exponent in Clinger's exact range -> one IEEE multiply or divide.
+//                Digits are converted four at a time (SWAR on one 32-bit word);
 //   anything else: the field's extent is found and the general parser decides (and reports errors).
 // Returns true when the delimiter ended the row.
 __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, int* pp, uint64_t* bits_out,
                                               unsigned long long* status, int64_t t0) {
     const int fs = *pp;
-    const uint8_t* q = reg + fs;
-    unsigned c = *q;
+    int p = fs;
+    uint32_t x = ms_load4(reg, p);
+    unsigned c = x & 0xffu;
     uint64_t bits = MS_NAN_BITS;
     if (!ms_is_delim(c)) {
         uint64_t sign = 0;
         if (c == '-') {
             sign = 0x8000000000000000ull;
-            c = *++q;
+            x = ms_load4(reg, ++p);
         }
-        uint32_t acc = 0;
-        int nsig = 0, nfrac = 0, ndig = 0;
+        uint64_t acc = 0;
+        int ndig = 0, nfrac = 0;
         bool dot = false;
         for (;;) {
-            const unsigned d = c - '0';
-            if (d <= 9u) {
-                ndig++;
-                nsig += (acc | d) != 0;
-                acc = acc * 10u + d;
-                nfrac += dot;
-            } else if (c == '.' && !dot) {
-                dot = true;
-            } else {
-                break;
+            const uint32_t t = x ^ 0x30303030u;
+            const uint32_t nd = ((t + 0x76767676u) | t) & 0x80808080u;  // bytes that are not digits
+            if (nd == 0) {
+                acc = acc * 10000ull + ms_digits4(t);
+                ndig += 4;
+                nfrac += dot ? 4 : 0;
+                p += 4;
+                x = ms_load4(reg, p);
+                continue;
             }
-            c = *++q;
+            const int j = (__ffs(nd) - 1) >> 3;  // digits before the first other byte: 0..3
+            if (j) {
+                acc = acc * (j == 1 ? 10ull : j == 2 ? 100ull : 1000ull) + ms_digits4(t << ((4 - j) << 3));
+                ndig += j;
+                nfrac += dot ? j : 0;
+            }
+            c = (x >> (j << 3)) & 0xffu;
+            p += j;
+            if (c == '.' && !dot) {
+                dot = true;
+                x = ms_load4(reg, ++p);
+                continue;
+            }
+            break;
         }
+        // c = reg[p]: the first byte that is neither a digit nor the (first) decimal point
         int ex = -nfrac;
-        bool ok = ndig > 0 && nsig <= 9;
+        bool ok = ndig > 0 && ndig <= 19;
         if (ok && (c | 0x20u) == 'e') {
             // exponent: at most three digits
-            const uint8_t* r = q + 1;
+            const uint8_t* r = reg + p + 1;
             unsigned cc = *r;
             bool eneg = false;
             if (cc == '-' || cc == '+') {
@@ -612,13 +640,13 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
             }
             if (nd >= 1 && nd <= 3 && ms_is_delim(cc)) {
                 ex += eneg ? -ev : ev;
-                q = r;
+                p = (int)(r - reg);
                 c = cc;
             } else {
                 ok = false;
             }
         }
-        if (ok && ms_is_delim(c) && (acc == 0 || (ex >= -22 && ex <= 22))) {
+        if (ok && ms_is_delim(c) && (acc == 0 || (acc <= (1ull << 53) && ex >= -22 && ex <= 22))) {
             if (acc == 0) {
                 bits = sign;
             } else {
@@ -628,8 +656,8 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
             }
         } else {
             // general path: [fs, fe) up to the next delimiter
-            while (!ms_is_delim(c)) c = *++q;
-            MsParsed pr = ms_parse_field_call(reg + fs, q);
+            while (!ms_is_delim(c)) c = reg[++p];
+            MsParsed pr = ms_parse_field_call(reg + fs, reg + p);
             bits = pr.bits;
             if (pr.status != MS_PARSE_OK) {
                 bits = MS_NAN_BITS;
@@ -639,7 +667,7 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
     }
     *bits_out = bits;
-    *pp = (int)(q - reg) + 1;
+    *pp = p + 1;
     return c != ',';
 }
 
@@ -652,7 +680,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 2)
     uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
     int* const row_start = reinterpret_cast<int*>(smem_raw + PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32);
     __shared__ int s_warp_terms[PARSE_WARPS];
-    __shared__ int s_lt_end;
+    __shared__ int s_lt_end, s_next_item;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
@@ -763,7 +791,10 @@ __global__ void __launch_bounds__(PARSE_THREADS, 2)
             const int bb = min(sec_b, ba + PARSE_ROWS_CAP - 1);
             const int nrows = bb - ba + 1;
             // ---- A4. start offset of rows ba .. bb+1 (the last one closes row bb)
-            if (tid == 0 && starts_at_t0 && ba == 0) row_start[0] = 0;
+            if (tid == 0) {
+                s_next_item = 0;
+                if (starts_at_t0 && ba == 0) row_start[0] = 0;
+            }
             {
                 int lt = lt0;
 #pragma unroll
@@ -781,15 +812,20 @@ __global__ void __launch_bounds__(PARSE_THREADS, 2)
 
             // ---- B. lanes = rows, lockstep over columns
             const int groups = (nrows + 31) >> 5;
-            int nchunks = (2 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 2 items per warp
+            int nchunks = (3 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 3 items per warp
             nchunks = max(1, min(nchunks, ncols / 4));
             const int cs = (ncols + nchunks - 1) / nchunks;  // columns per chunk
             nchunks = (ncols + cs - 1) / cs;
             const int items = groups * nchunks;
-            for (int item = warp; item < items; item += PARSE_WARPS) {
+            for (;;) {
+                // warps take (row group, column chunk) items from a shared counter
+                int item = 0;
+                if (lane == 0) item = atomicAdd(&s_next_item, 1);
+                item = __shfl_sync(0xffffffffu, item, 0);
+                if (item >= items) break;
                 const int g = item / nchunks, k = item - g * nchunks;
                 const int r = (g << 5) + lane;
-                if (r >= nrows) continue;
+                if (r < nrows) {
                 const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
                 int p = row_start[r];
                 bool done = false;
@@ -820,6 +856,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 2)
                     if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
                     const int ch = c - 2;
                     if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                }
                 }
             }
             __syncthreads();  // row_start is reused by the next batch
