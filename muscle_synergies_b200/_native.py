@@ -9,7 +9,7 @@ import os
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "libms_b200.so")
 
-MS_TILE_BYTES = 65536
+MS_TILE_BYTES = 49152
 MS_MAX_ROW_BYTES = 8192
 MS_MAX_BLANK_ROWS = 8
 MS_MAX_SECTIONS = 4

@@ -1,6 +1,6 @@
 // Vicon Nexus CSV loader kernels for sm_100a.
 //
-//   ms_scan_kernel     pass 1, one CTA per 64 KiB tile: row terminators, quotes, blank rows
+//   ms_scan_kernel     pass 1, one CTA per 48 KiB tile: row terminators, quotes, blank rows
 //   ms_resolve_kernel  single CTA: terminator prefix per tile, blank rows that straddle
 //                      tiles, their csv row indices -> ms_scan_summary
 //   ms_parse_kernel    pass 2, one CTA per tile: (row, column) of every field by a block-wide
@@ -111,7 +111,7 @@ struct MsWarpSummary {
     int first_term, last_term;            // tile-relative, -1 if none
 };
 
-// Each warp walks a contiguous 8 KiB span of the tile, 512 bytes (one coalesced 16-byte load per
+// Each warp walks a contiguous 6 KiB span of the tile, 512 bytes (one coalesced 16-byte load per
 // lane) per iteration, carrying the state of the row in progress in registers; the eight warp
 // summaries are combined once at the end.  The delimiter masks are written out so that pass 2
 // does not classify the bytes again.
@@ -510,11 +510,11 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 // ===================================================================================================
 // pass 2
 // ===================================================================================================
-// One CTA per 64 KiB tile; the CTA owns the rows that START inside the tile and reads up to
+// One CTA per 48 KiB tile (three CTAs per SM); the CTA owns the rows that START inside the tile and reads up to
 // MS_MAX_ROW_BYTES past it to finish the last one.
 //
 //   A. stage the bytes in shared memory (16-byte coalesced loads); per thread, comma and
-//      terminator bit masks of a contiguous 144-byte chunk; block-wide prefix sum of the
+//      terminator bit masks of a contiguous 112-byte chunk; block-wide prefix sum of the
 //      terminator counts -> start offset of every owned row (shared array); comma masks are kept
 //      in shared memory for step B's column lookups
 //   B. one LANE per row, lanes in lockstep over the columns: the 32 lanes of a warp parse the
@@ -530,7 +530,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 #define PARSE_THREADS 512
 #define PARSE_WARPS (PARSE_THREADS / 32)
 #define PARSE_REGION (MS_TILE_BYTES + MS_MAX_ROW_BYTES)  // bytes staged per CTA
-#define PARSE_CHUNK (PARSE_REGION / PARSE_THREADS)        // 144 bytes per thread: 128 + 16 -> conflict-free LDS.128
+#define PARSE_CHUNK (PARSE_REGION / PARSE_THREADS)        // 112 bytes per thread
 #define PARSE_SEGS (PARSE_CHUNK / 16)
 static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGION, "chunking");
 #define PARSE_PAD 16  // bytes staged before and after the region
@@ -671,7 +671,7 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
     return c != ',';
 }
 
-__global__ void __launch_bounds__(PARSE_THREADS, 2)
+__global__ void __launch_bounds__(PARSE_THREADS, 3)
     ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
                     const uint32_t* __restrict__ masks, const MsSectionsArg secs,
                     unsigned long long* __restrict__ status) {

@@ -45,6 +45,7 @@ from .header import (
 
 _TERMINATOR = re.compile(rb"\r\n|\r|\n")
 _HEADER_LINES = 5
+_header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 
 def _torch():
@@ -78,7 +79,7 @@ class _Source:
 
     def take_lines(self, offset: int, k: int) -> Tuple[bytes, int]:
         """Bytes of the first k physical lines starting at `offset` (fewer at EOF)."""
-        window = 1 << 16
+        window = 1 << 13
         while True:
             chunk = self.fetch(offset, window)
             ends = []
@@ -318,6 +319,12 @@ def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, m
     if want == 0:
         return None, b""
     chunk, n_lines = src.take_lines(offset, want)
+    cached = _header_cache.get((chunk, machine.expected, want)) if want == _HEADER_LINES else None
+    if cached is not None:
+        # identical header bytes (the usual case in a batch of trials): reuse the parsed layout
+        machine.layout = cached  # layouts are read-only once parsed
+        machine.next_line = None
+        return None, chunk
     rows, consumed = rows_from_bytes(chunk, want)
     if consumed != len(rows) or len(rows) != min(want, n_lines):
         raise NotImplementedError(
@@ -329,6 +336,8 @@ def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, m
             machine.feed(row)
         except Exception as exc:  # noqa: BLE001 - the reference wraps everything (load_csv.py:131)
             return wrap_error(first_row + i + 1, name, exc), chunk
+    if machine.done and len(_header_cache) < 64:
+        _header_cache[(chunk, machine.expected, want)] = machine.layout
     return None, chunk
 
 
