@@ -117,19 +117,36 @@ int ms_cut_windows(const double* d_src, int64_t src_stride, int32_t n_channels, 
                    const int64_t* d_stops, const int64_t* d_out_offsets, int32_t n_windows, double* d_out,
                    int64_t max_window_len, void* stream);
 
+/* ---- EMG envelope chain (float64, tolerance parity) ---------------- */
+
+/* zero_center (analysis.py:230-249): mean of each channel of a channel-major array. */
+int ms_channel_means(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, double* d_mean, void* stream);
+/* rms (analysis.py:435-507): sqrt(np.convolve((x - mean)^2, ones(window) / window, "same")) per
+ * channel; d_mean may be NULL (no centring).  window <= n. */
+int ms_rms_envelope(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const double* d_mean,
+                    int32_t window, double* d_out, int64_t out_stride, void* stream);
+/* time_normalize (analysis.py:551-594, linear) of rows [start_w, stop_w) onto reduce_to points,
+ * then (normalize != 0) normalize (analysis.py:510-525): divide by the column max |.|.
+ * d_out: [n_windows][reduce_to][n_channels] (samples x muscles, the orientation NMF takes). */
+int ms_time_normalize_windows(const double* d_env, int64_t stride, int32_t n_channels, const int64_t* d_starts,
+                              const int64_t* d_stops, int32_t n_windows, int32_t reduce_to, int32_t normalize,
+                              double* d_out, void* stream);
+
 /* ---- NMF by multiplicative updates (extension; not a reference-parity claim) --------------- */
 
 /* What analysis.py:862-863 asks scikit-learn for with solver="mu", beta_loss="frobenius":
  *   W <- W * (X H^T) / (W (H H^T));  H <- H * (W^T X) / ((W^T W) H);  zero denominators -> float32 eps;
  *   every check_every iterations (tol > 0) stop when (previous_error - error) / error_at_init < tol.
  * One launch runs a whole batch of problems on the same X (rank sweep x restarts), fp32,
- * X / W / H resident in shared memory.  d_X: [n][m] row-major (samples x muscles).
- * h_ranks[p]: rank of problem p (1..16).  d_W / d_H: initial factors packed problem after
- * problem (W_p [n][k_p], H_p [k_p][m], row-major); results overwrite them.  d_work:
- * n_problems * 24 bytes.  Outputs per problem: d_n_iter, d_err = ||X - W H||_F,
+ * X / W / H resident in shared memory.  d_X: one or more [n][m] row-major matrices (samples x
+ * muscles); h_x_index[p] (NULL = all 0) selects the matrix of problem p, so a launch can also
+ * cover many gait cycles.  h_ranks[p]: rank of problem p (1..16).  d_W / d_H: initial factors
+ * packed problem after problem (W_p [n][k_p], H_p [k_p][m], row-major); results overwrite them.
+ * d_work: n_problems * 32 bytes.  Outputs per problem: d_n_iter, d_err = ||X - W H||_F,
  * d_vaf [m + 1] = 1 - SS_res / SS_tot overall, then per column (analysis.py:642-667). */
 int32_t ms_nmf_resident_max_rows(int32_t m, int32_t kmax);
-int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_ranks, int32_t n_problems,
+int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_ranks, const int32_t* h_x_index,
+                      int32_t n_problems,
                       float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every, void* d_work,
                       int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
 

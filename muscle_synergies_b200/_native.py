@@ -65,9 +65,12 @@ def _declare(L):
         "ms_transitions_workspace_bytes": (i64, [i64]),
         "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),
         "ms_cut_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp]),
+        "ms_channel_means": (ctypes.c_int, [vp, i64, i32, i64, vp, vp]),
+        "ms_rms_envelope": (ctypes.c_int, [vp, i64, i32, i64, vp, i32, vp, i64, vp]),
+        "ms_time_normalize_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, i32, i32, i32, vp, vp]),
         "ms_nmf_resident_max_rows": (i32, [i32, i32]),
-        "ms_nmf_mu_batched": (ctypes.c_int, [vp, i32, i32, ctypes.POINTER(i32), i32, vp, vp, i32, ctypes.c_float, i32, vp,
-                                             vp, vp, vp, vp]),
+        "ms_nmf_mu_batched": (ctypes.c_int, [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, vp, i32,
+                                             ctypes.c_float, i32, vp, vp, vp, vp, vp]),
         "ms_last_cuda_error": (ctypes.c_char_p, []),
         "ms_version": (ctypes.c_char_p, []),
         "ms_launch_count": (i64, []),

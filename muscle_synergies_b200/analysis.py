@@ -45,11 +45,13 @@ def sklearn_random_init(X: np.ndarray, k: int, seed: int):
 
 
 def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int = 200, tol: float = 1e-4,
-                   check_every: int = 10, init=None, device=None) -> NMFBatchResult:
-    """Runs len(ranks) MU factorisations of the same non-negative X (n samples x m muscles).
+                   check_every: int = 10, init=None, device=None, x_index: Optional[Sequence[int]] = None) -> NMFBatchResult:
+    """Runs len(ranks) MU factorisations in one kernel launch.
 
-    ranks[p], seeds[p]: rank and sklearn `random_state` of problem p; `init` optionally gives
-    the initial (W, H) pairs instead of the seeds.  Everything runs in one kernel launch."""
+    X: non-negative (n samples x m muscles), or a stack (B, n, m) of such matrices (e.g. one per
+    gait cycle) with x_index[p] naming the matrix of problem p.  ranks[p], seeds[p]: rank and
+    sklearn `random_state` of problem p; `init` optionally gives the initial (W, H) pairs
+    instead of the seeds."""
     import torch
 
     lib = nat.lib()
@@ -60,14 +62,19 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         Xh = X.detach().to("cpu", torch.float64).numpy()
     else:
         Xh = np.asarray(X, dtype=np.float64)
-    if Xh.ndim != 2 or Xh.size == 0:
-        raise ValueError("X must be a non-empty 2-D array")
+    if Xh.ndim == 2:
+        Xh = Xh[None]
+    if Xh.ndim != 3 or Xh.size == 0:
+        raise ValueError("X must be a non-empty (n, m) matrix or a (B, n, m) stack")
     if (Xh < 0).any():
         raise ValueError("Negative values in data passed to NMF (input X)")
-    n, m = Xh.shape
+    _, n, m = Xh.shape
     ranks = np.asarray(ranks, dtype=np.int32)
     seeds = np.asarray(seeds, dtype=np.int64)
     P = len(ranks)
+    xi = np.zeros(P, dtype=np.int32) if x_index is None else np.asarray(x_index, dtype=np.int32)
+    if len(xi) != P or len(seeds) != P or xi.min() < 0 or xi.max() >= Xh.shape[0]:
+        raise ValueError("ranks, seeds and x_index must have one entry per problem")
     kmax = int(ranks.max())
     if n > int(lib.ms_nmf_resident_max_rows(m, kmax)):
         raise NotImplementedError(f"X with {n} rows does not fit the shared-memory resident NMF kernel")
@@ -76,7 +83,7 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         if init is not None:
             W0, H0 = init[p]
         else:
-            W0, H0 = sklearn_random_init(Xh, int(ranks[p]), int(seeds[p]))  # float64 draws, like sklearn
+            W0, H0 = sklearn_random_init(Xh[xi[p]], int(ranks[p]), int(seeds[p]))  # float64 draws, like sklearn
         w_parts.append(np.ascontiguousarray(W0, dtype=np.float32).ravel())
         h_parts.append(np.ascontiguousarray(H0, dtype=np.float32).ravel())
     stream = torch.cuda.current_stream(dev)
@@ -84,14 +91,15 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         dX = torch.from_numpy(np.ascontiguousarray(Xh, dtype=np.float32)).to(dev)
         dW = torch.from_numpy(np.concatenate(w_parts)).to(dev)
         dH = torch.from_numpy(np.concatenate(h_parts)).to(dev)
-        work = torch.empty(P * 24, dtype=torch.uint8, device=dev)
+        work = torch.empty(P * 32, dtype=torch.uint8, device=dev)
         d_iter = torch.empty(P, dtype=torch.int32, device=dev)
         d_err = torch.empty(P, dtype=torch.float32, device=dev)
         d_vaf = torch.empty((P, m + 1), dtype=torch.float32, device=dev)
         h_ranks = (ctypes.c_int32 * P)(*[int(k) for k in ranks])
+        h_xi = (ctypes.c_int32 * P)(*[int(v) for v in xi])
         nat.check(
             lib.ms_nmf_mu_batched(
-                dX.data_ptr(), n, m, h_ranks, P, dW.data_ptr(), dH.data_ptr(), int(max_iter), ctypes.c_float(tol),
+                dX.data_ptr(), n, m, h_ranks, h_xi, P, dW.data_ptr(), dH.data_ptr(), int(max_iter), ctypes.c_float(tol),
                 int(check_every), work.data_ptr(), d_iter.data_ptr(), d_err.data_ptr(), d_vaf.data_ptr(),
                 ctypes.c_void_p(stream.cuda_stream),
             ),

@@ -31,6 +31,7 @@ struct MsNmfProblem {
     int k;
     long long w_off;  // floats from d_W to this problem's W [n][k]
     long long h_off;  // floats from d_H to this problem's H [k][m]
+    long long x_off;  // floats from d_X to this problem's X [n][m]
 };
 
 __device__ __forceinline__ float ms_block_sum(float v, float* s_red) {
@@ -221,7 +222,7 @@ __global__ void __launch_bounds__(NMF_THREADS)
     extern __shared__ float sm[];
     const MsNmfProblem pb = problems[blockIdx.x];
     MsNmfArgs A;
-    A.X = X;
+    A.X = X + pb.x_off;
     A.n = n;
     A.m = m;
     A.Wp = Wg + pb.w_off;
@@ -260,10 +261,12 @@ extern "C" int32_t ms_nmf_resident_max_rows(int32_t m, int32_t kmax) {
     return (int32_t)((budget - fixed) / per_row);
 }
 
-// h_ranks[P]: rank of each problem.  d_W / d_H hold the initial factors packed problem after
-// problem (W_p is [n][k_p] row-major, H_p is [k_p][m]) and receive the results in place.
-// d_work: P * 24 bytes.  d_vaf: [P][m + 1] (overall, then per column).
-extern "C" int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_ranks, int32_t n_problems,
+// h_ranks[P]: rank of each problem; h_x_index[P] (may be NULL = all 0): which [n][m] matrix of d_X
+// problem p factorises.  d_W / d_H hold the initial factors packed problem after problem (W_p is
+// [n][k_p] row-major, H_p is [k_p][m]) and receive the results in place.
+// d_work: P * 32 bytes.  d_vaf: [P][m + 1] (overall, then per column).
+extern "C" int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_ranks,
+                                 const int32_t* h_x_index, int32_t n_problems,
                                  float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every, void* d_work,
                                  int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream) {
     if (!d_X || !h_ranks || !d_W || !d_H || !d_work || !d_n_iter || !d_err || !d_vaf) return MS_E_INVALID;
@@ -283,6 +286,11 @@ extern "C" int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const i
         h[p].k = k;
         h[p].w_off = wo;
         h[p].h_off = ho;
+        h[p].x_off = h_x_index ? (long long)h_x_index[p] * n * m : 0;
+        if (h[p].x_off < 0) {
+            free(h);
+            return MS_E_INVALID;
+        }
         wo += (long long)n * k;
         ho += (long long)k * m;
         if (k > kmax) kmax = k;

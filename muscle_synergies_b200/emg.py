@@ -1,0 +1,130 @@
+"""EMG envelope chain on the GPU (SURVEY.md section 8f, rank 1 "next" row).
+
+Mirrors of the reference's preprocessing functions (src/muscle_synergies/analysis.py):
+`zero_center` (:230-249), `rms` (:435-507), `normalize` (:510-525), `time_normalize`
+(:551-594, kind="linear"), same signatures on DataFrames, plus `envelope_windows`, which keeps
+everything in HBM between the cut windows and the NMF stage: trial-wide zero-centred moving RMS,
+then per window linear time-normalisation to `reduce_to` samples and division by the column
+maximum - the flow of docs/source/tutorials "Finding muscle synergies" (cells 10-23) applied
+per gait cycle.  float64; parity with the reference functions is to a tolerance (sums are
+ordered differently), see tests/test_emg_gpu.py.
+"""
+import ctypes
+from typing import Optional, Sequence, Union
+
+import numpy as np
+import pandas
+
+from . import _native as nat
+
+
+def _torch():
+    import torch
+
+    if not torch.cuda.is_available():
+        raise nat.NativeError("muscle_synergies_b200.emg needs a CUDA device; there is no CPU fallback")
+    return torch
+
+
+def _stream(torch, dev):
+    return ctypes.c_void_p(torch.cuda.current_stream(dev).cuda_stream)
+
+
+def _channel_major(signal_df: pandas.DataFrame):
+    torch = _torch()
+    arr = np.ascontiguousarray(signal_df.to_numpy(dtype=np.float64).T)  # (channels, rows)
+    return torch.from_numpy(arr).cuda()
+
+
+def channel_means(x):
+    """Mean of every row of a (channels, samples) float64 CUDA tensor."""
+    torch = _torch()
+    x = x if x.stride(1) == 1 else x.contiguous()
+    out = torch.empty(x.shape[0], dtype=torch.float64, device=x.device)
+    nat.check(nat.lib().ms_channel_means(x.data_ptr(), int(x.stride(0)), int(x.shape[0]), int(x.shape[1]), out.data_ptr(),
+                                         _stream(torch, x.device)), "ms_channel_means")
+    return out
+
+
+def rms_envelope(x, window: int, mean=None):
+    """sqrt(convolve((x - mean)^2, ones(window)/window, "same")) per row of a (channels, samples) tensor."""
+    torch = _torch()
+    x = x if x.stride(1) == 1 else x.contiguous()
+    n_ch, n = int(x.shape[0]), int(x.shape[1])
+    if window < 1 or window > n:
+        raise ValueError("window must be between 1 and the number of samples")
+    out = torch.empty((n_ch, n), dtype=torch.float64, device=x.device)
+    nat.check(
+        nat.lib().ms_rms_envelope(x.data_ptr(), int(x.stride(0)), n_ch, n, mean.data_ptr() if mean is not None else None,
+                                  int(window), out.data_ptr(), n, _stream(torch, x.device)),
+        "ms_rms_envelope",
+    )
+    return out
+
+
+def time_normalize_windows(env, starts: Sequence[int], stops: Sequence[int], reduce_to: int, normalize: bool = True):
+    """(n_windows, reduce_to, channels) float64 CUDA tensor from a (channels, samples) envelope."""
+    torch = _torch()
+    env = env if env.stride(1) == 1 else env.contiguous()
+    n_ch = int(env.shape[0])
+    meta = torch.tensor([list(starts), list(stops)], dtype=torch.int64).to(env.device)
+    out = torch.empty((len(starts), reduce_to, n_ch), dtype=torch.float64, device=env.device)
+    nat.check(
+        nat.lib().ms_time_normalize_windows(env.data_ptr(), int(env.stride(0)), n_ch, meta[0].data_ptr(), meta[1].data_ptr(),
+                                            len(starts), int(reduce_to), int(bool(normalize)), out.data_ptr(),
+                                            _stream(torch, env.device)),
+        "ms_time_normalize_windows",
+    )
+    return out
+
+
+def envelope_windows(device, windows, window_size: float = 0.5, reduce_to: int = 200, normalize: bool = True):
+    """Trial-wide zero-centred RMS envelope of a DeviceData (EMG), then every (frame, subframe)
+    window resampled to `reduce_to` points and amplitude-normalised.  Stays on the GPU.
+
+    Returns (n_windows, reduce_to, n_muscles) float64 - each [w] is the X of one NMF problem."""
+    x = device.tensor
+    n = int(x.shape[1])
+    win = round(window_size * device.sampling_frequency)
+    mean = channel_means(x)
+    env = rms_envelope(x, win, mean)
+    idx = [device.to_index(w) for w in windows]
+    starts = [s.indices(n)[0] for s in idx]
+    stops = [max(s.indices(n)[0], s.indices(n)[1]) for s in idx]
+    return time_normalize_windows(env, starts, stops, reduce_to, normalize)
+
+
+# ---- DataFrame-level mirrors of the reference API ----------------------------------------------------------
+def _like(signal_df: pandas.DataFrame, inplace: bool, values: np.ndarray) -> pandas.DataFrame:
+    if inplace:
+        signal_df.iloc[:, :] = values
+        return signal_df
+    return pandas.DataFrame(values, index=signal_df.index, columns=signal_df.columns)
+
+
+def zero_center(signal_df: pandas.DataFrame, inplace: bool = False) -> pandas.DataFrame:
+    x = _channel_major(signal_df)
+    centred = x - channel_means(x)[:, None]
+    return _like(signal_df, inplace, centred.T.cpu().numpy())
+
+
+def rms(signal_df: pandas.DataFrame, window_size: Union[int, float], inplace: bool = False,
+        sampling_frequency: Optional[int] = None) -> pandas.DataFrame:
+    if sampling_frequency is not None:
+        window_size = round(window_size * sampling_frequency)
+    out = rms_envelope(_channel_major(signal_df), int(window_size))
+    return _like(signal_df, inplace, out.T.cpu().numpy())
+
+
+def normalize(signal_df: pandas.DataFrame, inplace: bool = False) -> pandas.DataFrame:
+    x = _channel_major(signal_df)
+    out = x / x.abs().amax(dim=1, keepdim=True)
+    return _like(signal_df, inplace, out.T.cpu().numpy())
+
+
+def time_normalize(signal_df: pandas.DataFrame, reduce_to: int, kind="linear", fill_value="extrapolate") -> pandas.DataFrame:
+    if kind != "linear":
+        raise NotImplementedError('the CUDA stage implements kind="linear" only')
+    x = _channel_major(signal_df)
+    out = time_normalize_windows(x, [0], [int(x.shape[1])], reduce_to, normalize=False)[0]
+    return pandas.DataFrame(out.cpu().numpy(), index=np.linspace(0, 1, reduce_to), columns=signal_df.columns)

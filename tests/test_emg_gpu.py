@@ -1,0 +1,60 @@
+"""EMG envelope chain against the numpy/scipy oracle that makes the
+reference's own calls.  float64, stated tolerance: relative 1e-9 (sums are ordered differently)."""
+import numpy as np
+import pandas as pd
+import pytest
+
+pytestmark = pytest.mark.gpu
+RTOL = 1e-9
+
+
+@pytest.fixture(scope="module")
+def emg():
+    import __graft_entry__ as g
+
+    g.build()
+    from muscle_synergies_b200 import emg
+
+    return emg
+
+
+def test_dataframe_level_functions(emg):
+    from oracle import emg_oracle as eo
+
+    rng = np.random.default_rng(1)
+    x = rng.normal(0.002, 0.01, (7001, 5))
+    df = pd.DataFrame(x, columns=list("abcde"))
+    np.testing.assert_allclose(emg.zero_center(df).to_numpy(), eo.zero_center(x), rtol=RTOL, atol=1e-15)
+    for win in (1, 2, 7, 1000, 1001, 7001):
+        np.testing.assert_allclose(emg.rms(df, win).to_numpy(), eo.rms(x, win), rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(emg.rms(df, 0.5, sampling_frequency=2000).to_numpy(), eo.rms(x, 1000), rtol=RTOL, atol=1e-13)
+    np.testing.assert_allclose(emg.normalize(df).to_numpy(), eo.normalize(x), rtol=RTOL)
+    for r in (2, 200, 7001, 9000):
+        got = emg.time_normalize(df, r)
+        np.testing.assert_allclose(got.to_numpy(), eo.time_normalize(x, r), rtol=RTOL, atol=1e-15)
+        assert list(got.columns) == list(df.columns) and np.allclose(got.index, np.linspace(0, 1, r))
+    inplace = df.copy()
+    assert emg.zero_center(inplace, inplace=True) is inplace
+    with pytest.raises(NotImplementedError):
+        emg.time_normalize(df, 10, kind="cubic")
+
+
+def test_envelope_windows_on_a_segmented_trial(emg):
+    """Load -> segment -> per-cycle envelopes on the GPU, against the oracle on the host arrays."""
+    import muscle_synergies_b200 as ms
+    from muscle_synergies_b200.segment import Cycle, Segmenter, Trecho
+    from oracle import emg_oracle as eo
+    from tools.synth_vicon import synth_layout
+
+    data = ms.load_vicon_bytes(synth_layout("D", seed=0), name="D")
+    seg = Segmenter(data)
+    windows = [seg.get_times_of(t, c) for t in Trecho for c in Cycle]
+    got = emg.envelope_windows(data.emg, windows, window_size=0.5, reduce_to=200).cpu().numpy()
+    ranges = []
+    for w in windows:
+        sl = data.emg.to_index(w)
+        ranges.append((sl.start, sl.stop))
+    want = eo.envelope_windows(data.emg.df.to_numpy(), ranges, 1000, 200)
+    assert got.shape == want.shape == (8, 200, 8)
+    np.testing.assert_allclose(got, want, rtol=1e-8, atol=1e-12)
+    assert np.abs(got).max() <= 1.0 + 1e-12

@@ -126,3 +126,31 @@ def test_other_shapes(analysis):
         W, H, _ = no.mu(X, W0, H0, max_iter=60, tol=0.0)
         want_all, want_cols = no.vaf(X, W, H)
         assert abs(res.vaf[0, 0] - want_all) <= VAF_TOL and np.abs(res.vaf[0, 1:] - want_cols).max() <= 5 * VAF_TOL
+
+
+def test_end_to_end_cycles_to_synergies(analysis):
+    """BASELINE configs[4] in miniature: load -> segment -> per-cycle envelopes -> NMF sweep over
+    every cycle in ONE launch; each problem checked against sklearn on the same envelope."""
+    import muscle_synergies_b200 as ms
+    from muscle_synergies_b200 import emg
+    from muscle_synergies_b200.segment import Cycle, Segmenter, Trecho
+    from oracle import nmf_oracle as no
+    from tools.synth_vicon import synth_layout
+
+    data = ms.load_vicon_bytes(synth_layout("D", seed=0), name="D")
+    seg = Segmenter(data)
+    windows = [seg.get_times_of(t, c) for t in Trecho for c in Cycle]
+    X = emg.envelope_windows(data.emg, windows, window_size=0.05, reduce_to=200)  # (8 cycles, 200, 8 muscles)
+    assert X.shape == (8, 200, 8) and float(X.min()) >= 0.0
+    ranks, seeds, xi = [], [], []
+    for cyc in range(8):
+        for k in (1, 2, 3, 4):
+            for r in range(3):
+                ranks.append(k), seeds.append(r), xi.append(cyc)
+    res = analysis.nmf_mu_batched(X, ranks, seeds, max_iter=150, tol=0.0, x_index=xi)
+    Xh = X.cpu().numpy()
+    for p in range(0, len(ranks), 5):
+        W, H, _ = sklearn_run(Xh[xi[p]], ranks[p], seeds[p], 150, 0.0)
+        want_all, want_cols = no.vaf(Xh[xi[p]], W, H)
+        assert abs(res.vaf[p, 0] - want_all) <= VAF_TOL
+        assert np.abs(res.vaf[p, 1:] - want_cols).max() <= 2 * VAF_TOL
