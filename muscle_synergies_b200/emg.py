@@ -32,7 +32,7 @@ def _stream(torch, dev):
 
 def _channel_major(signal_df: pandas.DataFrame):
     torch = _torch()
-    arr = np.ascontiguousarray(signal_df.to_numpy(dtype=np.float64).T)  # (channels, rows)
+    arr = np.array(signal_df.to_numpy(dtype=np.float64).T, order="C", copy=True)  # (channels, rows)
     return torch.from_numpy(arr).cuda()
 
 
