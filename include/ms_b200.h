@@ -150,6 +150,15 @@ int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_r
                       float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every, void* d_work,
                       int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
 
+/* Same contract for X of any length: X [n][m] and W [n][k] stream from HBM once per iteration
+ * (algorithmic bytes per iteration and problem: 4 n m + 8 n k); W^T X and W^T W are reduced per
+ * CTA and accumulated with atomics; the objective needs no extra pass over X.
+ * d_work: ms_nmf_stream_workspace_bytes(m, n_problems). */
+int64_t ms_nmf_stream_workspace_bytes(int32_t m, int32_t n_problems);
+int ms_nmf_mu_stream(const float* d_X, int64_t n, int32_t m, const int32_t* h_ranks, const int32_t* h_x_index,
+                     int32_t n_problems, float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every,
+                     void* d_work, int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
+
 /* ---- misc ------------------------------------------------------------------------------- */
 const char* ms_last_cuda_error(void);
 const char* ms_version(void);

@@ -45,13 +45,14 @@ def sklearn_random_init(X: np.ndarray, k: int, seed: int):
 
 
 def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int = 200, tol: float = 1e-4,
-                   check_every: int = 10, init=None, device=None, x_index: Optional[Sequence[int]] = None) -> NMFBatchResult:
+                   check_every: int = 10, init=None, device=None, x_index: Optional[Sequence[int]] = None,
+                   regime: Optional[str] = None) -> NMFBatchResult:
     """Runs len(ranks) MU factorisations in one kernel launch.
 
     X: non-negative (n samples x m muscles), or a stack (B, n, m) of such matrices (e.g. one per
     gait cycle) with x_index[p] naming the matrix of problem p.  ranks[p], seeds[p]: rank and
     sklearn `random_state` of problem p; `init` optionally gives the initial (W, H) pairs
-    instead of the seeds."""
+    instead of the seeds.  regime: None (by size), "resident" or "stream"."""
     import torch
 
     lib = nat.lib()
@@ -76,8 +77,8 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
     if len(xi) != P or len(seeds) != P or xi.min() < 0 or xi.max() >= Xh.shape[0]:
         raise ValueError("ranks, seeds and x_index must have one entry per problem")
     kmax = int(ranks.max())
-    if n > int(lib.ms_nmf_resident_max_rows(m, kmax)):
-        raise NotImplementedError(f"X with {n} rows does not fit the shared-memory resident NMF kernel")
+    # short signals stay resident in shared memory; long ones stream from HBM every iteration
+    resident = (n <= int(lib.ms_nmf_resident_max_rows(m, kmax))) if regime is None else (regime == "resident")
     w_parts, h_parts = [], []
     for p in range(P):
         if init is not None:
@@ -91,19 +92,20 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         dX = torch.from_numpy(np.ascontiguousarray(Xh, dtype=np.float32)).to(dev)
         dW = torch.from_numpy(np.concatenate(w_parts)).to(dev)
         dH = torch.from_numpy(np.concatenate(h_parts)).to(dev)
-        work = torch.empty(P * 32, dtype=torch.uint8, device=dev)
+        work = torch.empty(max(P * 32, int(lib.ms_nmf_stream_workspace_bytes(m, P))), dtype=torch.uint8, device=dev)
         d_iter = torch.empty(P, dtype=torch.int32, device=dev)
         d_err = torch.empty(P, dtype=torch.float32, device=dev)
         d_vaf = torch.empty((P, m + 1), dtype=torch.float32, device=dev)
         h_ranks = (ctypes.c_int32 * P)(*[int(k) for k in ranks])
         h_xi = (ctypes.c_int32 * P)(*[int(v) for v in xi])
+        entry = lib.ms_nmf_mu_batched if resident else lib.ms_nmf_mu_stream
         nat.check(
-            lib.ms_nmf_mu_batched(
+            entry(
                 dX.data_ptr(), n, m, h_ranks, h_xi, P, dW.data_ptr(), dH.data_ptr(), int(max_iter), ctypes.c_float(tol),
                 int(check_every), work.data_ptr(), d_iter.data_ptr(), d_err.data_ptr(), d_vaf.data_ptr(),
                 ctypes.c_void_p(stream.cuda_stream),
             ),
-            "ms_nmf_mu_batched",
+            "ms_nmf_mu_batched" if resident else "ms_nmf_mu_stream",
         )
         Wall, Hall = dW.cpu().numpy(), dH.cpu().numpy()
         n_iter, err, vafs = d_iter.cpu().numpy(), d_err.cpu().numpy(), d_vaf.cpu().numpy()

@@ -154,3 +154,31 @@ def test_end_to_end_cycles_to_synergies(analysis):
         want_all, want_cols = no.vaf(Xh[xi[p]], W, H)
         assert abs(res.vaf[p, 0] - want_all) <= VAF_TOL
         assert np.abs(res.vaf[p, 1:] - want_cols).max() <= 2 * VAF_TOL
+
+
+@pytest.mark.parametrize("n,k", [(200, 3), (5000, 4), (60001, 8)])
+def test_streaming_regime_matches_sklearn_and_the_resident_kernel(analysis, n, k):
+    """Long signals: X and W stream from HBM every iteration (ms_nmf_mu_stream)."""
+    from oracle import nmf_oracle as no
+
+    X = envelopes(5, n=n)
+    res = analysis.nmf_mu_batched(X, [k, k, 2], [0, 1, 0], max_iter=40, tol=0.0, regime="stream")
+    assert (res.n_iter == 40).all()
+    for p, (kk, seed) in enumerate([(k, 0), (k, 1), (2, 0)]):
+        W, H, model = sklearn_run(X, kk, seed, 40, 0.0)
+        want_all, want_cols = no.vaf(X, W, H)
+        assert abs(res.vaf[p, 0] - want_all) <= VAF_TOL
+        assert np.abs(res.vaf[p, 1:] - want_cols).max() <= 2 * VAF_TOL
+        assert abs(res.err[p] - model.reconstruction_err_) / np.linalg.norm(X) <= ERR_TOL
+    if n <= 5000:
+        same = analysis.nmf_mu_batched(X, [k, k, 2], [0, 1, 0], max_iter=40, tol=0.0, regime="resident")
+        assert np.abs(same.vaf - res.vaf).max() <= 2e-5
+
+
+def test_streaming_regime_convergence_stop(analysis):
+    X = envelopes(6, n=3000)
+    res = analysis.nmf_mu_batched(X, [3], [2], max_iter=4000, tol=1e-5, regime="stream")
+    W, H, model = sklearn_run(X, 3, 2, 4000, 1e-5)
+    assert res.n_iter[0] % 10 == 0
+    assert abs(int(res.n_iter[0]) - model.n_iter_) <= max(60, 0.25 * model.n_iter_)
+    assert abs(res.err[0] - model.reconstruction_err_) / np.linalg.norm(X) <= ERR_TOL
