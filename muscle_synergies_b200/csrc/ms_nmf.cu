@@ -432,7 +432,6 @@ __global__ void __launch_bounds__(128)
                            MsNmfStreamState* __restrict__ states, const float* __restrict__ xx, int mode, int iteration,
                            float tol, int check_every) {
     __shared__ float sH[NMF_MAX_K * NMF_MAX_M];
-    __shared__ float s_red[4];
     const MsNmfProblem pb = problems[blockIdx.x];
     MsNmfStreamState* stt = states + blockIdx.x;
     const int k = pb.k, tid = threadIdx.x;
@@ -490,7 +489,6 @@ __global__ void __launch_bounds__(128)
         __syncthreads();
     }
     for (int e = tid; e < k * k + k * m; e += 128) stt->acc[e] = 0.f;
-    (void)s_red;
 }
 
 // sum of squares of every column of X (per problem's X) and of the residual X - W H: VAF
