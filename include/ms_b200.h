@@ -85,10 +85,20 @@ typedef struct ms_section {
 /* Bytes of device workspace needed to scan + parse a buffer of n_bytes. */
 int64_t ms_workspace_bytes(int64_t n_bytes);
 
+/* Offset in the workspace of the per-16-byte delimiter masks ms_scan leaves behind (uint32 per
+ * segment: row-terminator bits | comma bits << 16); lets a caller map a byte offset to its row. */
+int64_t ms_workspace_masks_offset(int64_t n_bytes);
+
 /* Pass 1: row terminators per tile, blank rows, quote count.  d_bytes must be 16-byte
  * aligned and readable up to n_bytes rounded up to 16 (pad the allocation). */
 int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
             ms_scan_summary* d_summary, void* stream);
+
+/* Rescan for buffers whose DATA rows contain '"' (ms_scan counted more quotes than the header
+ * lines hold): same outputs, but commas and line ends inside quoted fields (csv excel dialect,
+ * load_csv.py:30) are not delimiters.  Call after ms_scan, same buffer and workspace. */
+int ms_scan_quoted(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+                   ms_scan_summary* d_summary, void* stream);
 
 /* Pass 2: parse the data rows of up to MS_MAX_SECTIONS sections into channel-major
  * float64 arrays.  Needs the workspace filled by ms_scan for the same buffer.

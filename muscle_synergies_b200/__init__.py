@@ -11,6 +11,8 @@ there is no CPU fallback.
 """
 __version__ = "0.1.0"
 
+from .analysis import SynergyRunResult, find_synergies, nmf_mu_batched, vaf  # noqa: F401
+from .emg import envelope_windows, normalize, rms, time_normalize, zero_center  # noqa: F401
 from .vicon_data import (  # noqa: F401
     DeviceData,
     DeviceType,
@@ -27,4 +29,14 @@ __all__ = (
     "ViconNexusData",
     "DeviceData",
     "DeviceType",
+    # analysis.py names of the reference that have a CUDA implementation here
+    "zero_center",
+    "rms",
+    "normalize",
+    "time_normalize",
+    "vaf",
+    "find_synergies",
+    # extensions
+    "nmf_mu_batched",
+    "envelope_windows",
 )

@@ -60,7 +60,9 @@ def _declare(L):
     vp, i64, i32 = ctypes.c_void_p, ctypes.c_int64, ctypes.c_int32
     sigs = {
         "ms_workspace_bytes": (i64, [i64]),
+        "ms_workspace_masks_offset": (i64, [i64]),
         "ms_scan": (ctypes.c_int, [vp, i64, vp, i64, vp, vp]),
+        "ms_scan_quoted": (ctypes.c_int, [vp, i64, vp, i64, vp, vp]),
         "ms_parse": (ctypes.c_int, [vp, i64, vp, ctypes.POINTER(Section), i32, vp, vp]),
         "ms_transitions_workspace_bytes": (i64, [i64]),
         "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),

@@ -43,24 +43,36 @@ struct MsWorkspaceView {
     MsTileInfo* tiles;
     unsigned long long* term_prefix;  // terminator ends before the tile
     uint32_t* masks;                  // per 16-byte segment: terminator-end bits | comma bits << 16
+    uint8_t* tile_in_quote;           // quote-aware rescan only: csv in-quote state at the start of each tile
 };
 
 __host__ __device__ static inline int64_t ms_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
-static MsWorkspaceView ms_view(void* ws, int64_t n_tiles) {
+static MsWorkspaceView ms_view(void* ws, int64_t n_tiles, int64_t n_bytes_for_view) {
     MsWorkspaceView v;
     v.tiles = (MsTileInfo*)ws;
     char* p = (char*)ws + ms_align_up(n_tiles * (int64_t)sizeof(MsTileInfo), 256);
     v.term_prefix = (unsigned long long*)p;
     p += ms_align_up((n_tiles + 1) * 8, 256);
     v.masks = (uint32_t*)p;
+    p += ms_align_up((n_bytes_for_view + 15) / 16 * 4 + 32, 256);
+    v.tile_in_quote = (uint8_t*)p;
     return v;
+}
+
+// Byte offset, inside the workspace, of the per-16-byte delimiter masks written by ms_scan
+// (uint32: terminator-end bits | comma bits << 16) - used by the host to locate a row from a
+// byte offset on the error path.
+extern "C" int64_t ms_workspace_masks_offset(int64_t n_bytes) {
+    int64_t t = ms_num_tiles(n_bytes < 1 ? 1 : n_bytes);
+    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256);
 }
 
 extern "C" int64_t ms_workspace_bytes(int64_t n_bytes) {
     int64_t t = ms_num_tiles(n_bytes < 1 ? 1 : n_bytes);
-    int64_t segs = (n_bytes < 1 ? 1 : n_bytes + 15) / 16 + 8;
-    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256) + ms_align_up(segs * 4, 256);
+    int64_t nb = n_bytes < 1 ? 1 : n_bytes;
+    return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256) +
+           ms_align_up((nb + 15) / 16 * 4 + 32, 256) + ms_align_up(t, 256);
 }
 
 // ---- shared helpers --------------------------------------------------------------------------------
@@ -90,9 +102,7 @@ __device__ __forceinline__ uint4 ms_load16(const uint8_t* __restrict__ src, int6
 // pass 1
 // ===================================================================================================
 #define SCAN_THREADS 256
-#define SCAN_WARPS (SCAN_THREADS / 32)
-#define SCAN_SPAN (MS_TILE_BYTES / SCAN_WARPS)  // bytes of the tile one warp walks
-#define SCAN_ITERS (SCAN_SPAN / 512)
+#define SCAN_WARPS_MAX (SCAN_THREADS / 32)
 
 struct MsRun {  // state of the row in progress
     uint32_t has_term;  // a terminator was seen (in the span this state summarises)
@@ -115,9 +125,18 @@ struct MsWarpSummary {
 // lane) per iteration, carrying the state of the row in progress in registers; the eight warp
 // summaries are combined once at the end.  The delimiter masks are written out so that pass 2
 // does not classify the bytes again.
-__global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __restrict__ src, int64_t n,
-                                                                MsTileInfo* __restrict__ tiles,
-                                                                uint32_t* __restrict__ masks) {
+//
+// QUOTES variant (rare: the buffer has '"' in its data rows): one warp walks the whole tile and
+// also carries the csv in-quote state (excel dialect: a quote toggles it, "" toggles twice), so
+// commas and line ends inside quoted fields are not delimiters.  tile_in_quote[t] is the state
+// at the first byte of tile t (parity of the quotes before it).
+template <int SCAN_WARPS, bool QUOTES>
+__global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t* __restrict__ src, int64_t n,
+                                                                   MsTileInfo* __restrict__ tiles,
+                                                                   uint32_t* __restrict__ masks,
+                                                                   const uint8_t* __restrict__ tile_in_quote) {
+    constexpr int SCAN_SPAN = MS_TILE_BYTES / SCAN_WARPS;  // bytes of the tile one warp walks
+    constexpr int SCAN_ITERS = SCAN_SPAN / 512;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
     const int64_t t0 = tile * (int64_t)MS_TILE_BYTES;
@@ -131,6 +150,8 @@ __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __
     MsRun run;  // warp-uniform: state at the start of the current iteration
     run.has_term = 0;
     run.nb_tail = 0;
+    uint32_t in_quote = 0;  // warp-uniform (QUOTES only): inside a quoted field at the start of the iteration
+    if (QUOTES) in_quote = tile_in_quote[tile];
     uint32_t my_nterm = 0, my_nquote = 0, my_flags = 0;
     int w_first = -1, w_last = -1;  // meaningful in the lane that sees them; reduced at the end
     uint32_t w_nb_head = 0;
@@ -142,28 +163,49 @@ __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __
         // beyond the end: commas (blank, not a terminator)
         const uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
-        uint32_t lf16 = 0, cr16 = 0, comma16 = 0, gt16 = 0, hib = 0;
+        uint32_t lf16 = 0, cr16 = 0, comma16 = 0, gt16 = 0, hib = 0, quote16 = 0;
 #pragma unroll
         for (int k = 0; k < 4; k++) {
             lf16 |= ms_gather4(ms_eq_flags(w[k], 0x0a0a0a0au)) << (4 * k);
             cr16 |= ms_gather4(ms_eq_flags(w[k], 0x0d0d0d0du)) << (4 * k);
             comma16 |= ms_gather4(ms_eq_flags(w[k], 0x2c2c2c2cu)) << (4 * k);
             gt16 |= ms_gather4(ms_ge_flags(w[k], 0x21212121u)) << (4 * k);
-            my_nquote += __popc(ms_eq_flags(w[k], 0x22222222u));
+            const uint32_t qf = ms_eq_flags(w[k], 0x22222222u);
+            my_nquote += __popc(qf);
+            if (QUOTES) quote16 |= ms_gather4(qf) << (4 * k);
             hib |= w[k];
         }
         if (hib & 0x80808080u) my_flags |= MS_TI_HIGH;
         if (cr16) my_flags |= MS_TI_HAS_CR;
+        if (QUOTES) {
+            // in-quote state of every byte: prefix parity of the quote bits, carried across lanes
+            uint32_t par = quote16;
+            par ^= par << 1;
+            par ^= par << 2;
+            par ^= par << 4;
+            par ^= par << 8;
+            par &= 0xffffu;  // bit i: parity of the quotes in bytes 0..i of this vector
+            const uint32_t lane_odd = __popc(quote16) & 1u;
+            const uint32_t odd_lanes = __ballot_sync(0xffffffffu, lane_odd);
+            const uint32_t before = (in_quote ^ (__popc(odd_lanes & ((1u << lane) - 1u)) & 1u)) ? 0xffffu : 0u;
+            const uint32_t inq = par ^ before;  // delimiters at set bits are inside a quoted field
+            in_quote ^= __popc(odd_lanes) & 1u;
+            lf16 &= ~inq;
+            cr16 &= ~inq;
+            gt16 = (gt16 | (comma16 & inq)) & ~quote16;  // a quoted comma is content, the quotes are not
+            comma16 &= ~inq;
+        }
         uint32_t nb = gt16 & ~comma16;
         if (~gt16 & ~lf16 & ~cr16 & 0xffffu) {
             // rare: spaces, tabs or control bytes - the exact str.strip() whitespace set decides
             const uint32_t ws = ms_mask16(ms_strip_space_flags(v.x), ms_strip_space_flags(v.y),
                                           ms_strip_space_flags(v.z), ms_strip_space_flags(v.w));
             nb = ~(ws | comma16) & 0xffffu;
+            if (QUOTES) nb &= ~quote16;
         }
         // byte after this vector: first byte of the next lane's vector
         uint32_t next_lf = __shfl_down_sync(0xffffffffu, lf16 & 1u, 1);
-        if (lane == 31) next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
+        if (lane == 31) next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;  // (a quoted "\r\n" never ends a vector pair-split: both bytes are masked)
         const uint32_t term = ms_term16(lf16, cr16, next_lf);
         if (off < n) {
             uint32_t cm = comma16;
@@ -307,6 +349,15 @@ __global__ void __launch_bounds__(SCAN_THREADS) ms_scan_kernel(const uint8_t* __
         ti.pad[0] = ti.pad[1] = 0;
         ti.flags = f;
         tiles[tile] = ti;
+    }
+}
+
+__global__ void ms_quote_parity_kernel(const MsTileInfo* __restrict__ tiles, int64_t n_tiles,
+                                       uint8_t* __restrict__ tile_in_quote) {
+    uint32_t p = 0;
+    for (int64_t t = 0; t < n_tiles; t++) {
+        tile_in_quote[t] = (uint8_t)p;
+        p ^= tiles[t].n_quotes & 1u;
     }
 }
 
@@ -559,6 +610,49 @@ __device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uin
 
 __device__ __forceinline__ bool ms_is_delim(unsigned c) { return c == ',' || c == '\n' || c == '\r'; }
 
+// A field that starts with '"' (excel dialect of csv.reader, load_csv.py:30): the content runs to
+// the closing quote, "" is a literal quote, and - csv is not strict - text after the closing
+// quote is appended up to the next delimiter.  *pp: the opening quote on entry, the field's
+// delimiter on return.  An empty content is an empty field (None -> NaN in the reference).
+#define MS_QUOTED_MAX 64
+__device__ __noinline__ MsParsed ms_parse_quoted_call(const uint8_t* __restrict__ reg, int* pp) {
+    uint8_t buf[MS_QUOTED_MAX];
+    int n = 0, q = *pp + 1;
+    bool too_long = false;
+    for (;;) {
+        unsigned c = reg[q];
+        if (q >= PARSE_REGION) break;  // unbalanced quote: stop at the end of the staged bytes
+        if (c == '"') {
+            if (reg[q + 1] != '"') {
+                q++;
+                break;
+            }
+            q++;
+        }
+        if (n < MS_QUOTED_MAX)
+            buf[n++] = (uint8_t)c;
+        else
+            too_long = true;
+        q++;
+    }
+    while (q < PARSE_REGION && !ms_is_delim(reg[q])) {
+        if (n < MS_QUOTED_MAX)
+            buf[n++] = reg[q];
+        else
+            too_long = true;
+        q++;
+    }
+    *pp = q;
+    MsParsed r;
+    r.bits = MS_NAN_BITS;
+    r.status = MS_PARSE_OK;
+    if (too_long)
+        r.status = MS_PARSE_BAD;
+    else if (n > 0)
+        r.status = ms_parse_field(buf, buf + n, &r.bits);
+    return r;
+}
+
 // Four bytes at an arbitrary offset of the staged region (little endian): two aligned word
 // loads and a funnel shift.
 __device__ __forceinline__ uint32_t ms_load4(const uint8_t* __restrict__ reg, int p) {
@@ -585,7 +679,16 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
     uint32_t x = ms_load4(reg, p);
     unsigned c = x & 0xffu;
     uint64_t bits = MS_NAN_BITS;
-    if (!ms_is_delim(c)) {
+    if (c == '"') {
+        MsParsed pr = ms_parse_quoted_call(reg, &p);
+        bits = pr.bits;
+        if (pr.status != MS_PARSE_OK) {
+            bits = MS_NAN_BITS;
+            atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
+                                  (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+        }
+        c = reg[p];
+    } else if (!ms_is_delim(c)) {
         uint64_t sign = 0;
         if (c == '-') {
             sign = 0x8000000000000000ull;
@@ -867,16 +970,25 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
 // ===================================================================================================
 // C ABI
 // ===================================================================================================
-extern "C" int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
-                       ms_scan_summary* d_summary, void* stream) {
+static int ms_scan_impl(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+                        ms_scan_summary* d_summary, void* stream, bool quoted) {
     if (!d_bytes || !d_workspace || !d_summary || n_bytes < 0) return MS_E_INVALID;
     if (((uintptr_t)d_bytes & 15) != 0) return MS_E_INVALID;
     if (workspace_bytes < ms_workspace_bytes(n_bytes)) return MS_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     const int64_t n_tiles = ms_num_tiles(n_bytes);
-    MsWorkspaceView v = ms_view(d_workspace, ms_num_tiles(n_bytes < 1 ? 1 : n_bytes));
+    const int64_t nb = n_bytes < 1 ? 1 : n_bytes;
+    MsWorkspaceView v = ms_view(d_workspace, ms_num_tiles(nb), nb);
     if (n_tiles > 0) {
-        ms_scan_kernel<<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks);
+        if (!quoted) {
+            ms_scan_kernel<SCAN_WARPS_MAX, false>
+                <<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, nullptr);
+        } else {
+            // in-quote state at every tile start from the quote counts of the plain scan
+            ms_quote_parity_kernel<<<1, 1, 0, st>>>(v.tiles, n_tiles, v.tile_in_quote);
+            MS_COUNT_LAUNCH();
+            ms_scan_kernel<1, true><<<(unsigned)n_tiles, 32, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, v.tile_in_quote);
+        }
         MS_COUNT_LAUNCH();
         MS_CUDA_CHECK(cudaGetLastError());
     }
@@ -884,6 +996,19 @@ extern "C" int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspac
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
+}
+
+extern "C" int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+                       ms_scan_summary* d_summary, void* stream) {
+    return ms_scan_impl(d_bytes, n_bytes, d_workspace, workspace_bytes, d_summary, stream, false);
+}
+
+// Second scan for buffers whose DATA rows contain '"' (ms_scan reported more quotes than the
+// header lines hold): same outputs, with commas and line ends inside quoted fields not counted
+// as delimiters.  Must follow ms_scan on the same buffer and workspace.
+extern "C" int ms_scan_quoted(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
+                              ms_scan_summary* d_summary, void* stream) {
+    return ms_scan_impl(d_bytes, n_bytes, d_workspace, workspace_bytes, d_summary, stream, true);
 }
 
 extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
@@ -906,7 +1031,7 @@ extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_w
     }
     if (n_tiles == 0 || arg.n == 0) return MS_OK;
     MS_CUDA_CHECK(cudaFuncSetAttribute(ms_parse_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, PARSE_SMEM));
-    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), ms_num_tiles(n_bytes < 1 ? 1 : n_bytes));
+    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), ms_num_tiles(n_bytes < 1 ? 1 : n_bytes), n_bytes < 1 ? 1 : n_bytes);
     ms_parse_kernel<<<(unsigned)n_tiles, PARSE_THREADS, PARSE_SMEM, st>>>(d_bytes, n_bytes, v.term_prefix, v.masks, arg,
                                                                            (unsigned long long*)d_status);
     MS_COUNT_LAUNCH();

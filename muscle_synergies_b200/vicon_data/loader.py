@@ -95,19 +95,29 @@ class _Source:
                 return chunk, len(ends) + (1 if tail else 0)
             window *= 4
 
-    def count_terminators_before(self, pos: int) -> int:
-        """csv row index of the row containing byte `pos` (error path only)."""
+    def locate_row(self, ws, pos: int):
+        """(csv row index, first byte, one past the terminator) of the row holding byte `pos`,
+        from the delimiter masks the scan kernel left in the workspace (error path only)."""
         torch = _torch()
-        total = 0
-        step = 1 << 28
-        for a in range(0, pos, step):
-            b = min(pos, a + step)
-            seg = self.d_bytes[a:b]
-            nxt = self.d_bytes[a + 1 : b + 1]
-            lf = seg == 10
-            cr = seg == 13
-            total += int(lf.sum().item()) + int((cr & (nxt != 10)).sum().item())
-        return total
+        lib = nat.lib()
+        off = int(lib.ms_workspace_masks_offset(self.n))
+        n_seg = (self.n + 15) // 16
+        masks = ws[off : off + 4 * n_seg].view(torch.int32)
+        seg = pos // 16
+        term = masks & 0xFFFF
+        bits = torch.zeros((), dtype=torch.int64, device=masks.device)
+        for k in range(16):  # popcount of the terminator bits before the segment of `pos`
+            bits += ((term[:seg] >> k) & 1).sum()
+        lo = max(0, seg - nat.MS_MAX_ROW_BYTES // 16 - 2)
+        hi = min(n_seg, seg + nat.MS_MAX_ROW_BYTES // 16 + 2)
+        window = term[lo:hi].cpu().numpy().astype(np.int64)
+        ends = [16 * (lo + i) + b for i, m in enumerate(window) for b in range(16) if (m >> b) & 1]
+        before = [e for e in ends if e < pos]
+        after = [e for e in ends if e >= pos]
+        row = int(bits.item()) + sum(1 for e in before if e >= 16 * seg)
+        start = before[-1] + 1 if before else (0 if lo == 0 else 16 * lo)
+        stop = after[0] + 1 if after else self.n
+        return row, start, stop
 
 
 class ViconLoader:
@@ -188,17 +198,17 @@ class ViconLoader:
                 d_bytes[:n].copy_(staging[:n], non_blocking=True)
         return self._run(_Source(d_bytes, n, host), name)
 
-    def _scan(self, src: _Source):
+    def _scan(self, src: _Source, ws=None):
+        """ms_scan (or, when `ws` holds a previous scan, the quote-aware ms_scan_quoted)."""
         torch = self.torch
         stream, sptr = self._stream_ptr()
         ws_bytes = int(self.lib.ms_workspace_bytes(src.n))
+        entry, what = (self.lib.ms_scan, "ms_scan") if ws is None else (self.lib.ms_scan_quoted, "ms_scan_quoted")
         with torch.cuda.stream(stream):
-            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            if ws is None:
+                ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
             d_summary = torch.empty(ctypes.sizeof(nat.ScanSummary), dtype=torch.uint8, device=self.device)
-            nat.check(
-                self.lib.ms_scan(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary.data_ptr(), sptr),
-                "ms_scan",
-            )
+            nat.check(entry(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary.data_ptr(), sptr), what)
             self._pinned_summary[: d_summary.numel()].copy_(d_summary, non_blocking=True)
         stream.synchronize()
         summary = nat.ScanSummary.from_buffer_copy(self._pinned_summary.numpy()[: d_summary.numel()].tobytes())
@@ -207,7 +217,12 @@ class ViconLoader:
     def _run(self, src: _Source, name: str) -> ViconNexusData:
         torch = self.torch
         summary, ws = self._scan(src)
-        plan = _plan(src, summary, name)
+        try:
+            plan = _plan(src, summary, name)
+        except _QuotedData:
+            # '"' in the data rows: rescan with the csv in-quote state, then plan again
+            summary, ws = self._scan(src, ws)
+            plan = _plan(src, summary, name, quoted=True)
         stream, sptr = self._stream_ptr()
 
         sections = (nat.Section * nat.MS_MAX_SECTIONS)()
@@ -238,7 +253,7 @@ class ViconLoader:
         stream.synchronize()
         key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
         if key != nat.MS_ERR_NONE:
-            _raise_device_error(src, plan, key, name)
+            _raise_device_error(src, plan, key, name, ws)
         if plan.deferred_error is not None:
             raise plan.deferred_error
         data = _build(plan, blocks)
@@ -341,7 +356,11 @@ def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, m
     return None, chunk
 
 
-def _plan(src: _Source, summary, name: str) -> _Plan:
+class _QuotedData(Exception):
+    """The data rows contain quote characters: the plain scan's delimiters cannot be trusted."""
+
+
+def _plan(src: _Source, summary, name: str, quoted: bool = False) -> _Plan:
     plan = _Plan()
     n_rows = int(summary.n_rows)
     if summary.flags & nat.MS_SCAN_BLANK_OVERFLOW:
@@ -376,14 +395,14 @@ def _plan(src: _Source, summary, name: str) -> _Plan:
     end1 = b1[0] if b1 is not None else n_rows
     plan.data_rows[0] = (_HEADER_LINES, end1)
     if b1 is None:
-        _check_quotes(summary, header_quotes, name)
+        _check_quotes(summary, header_quotes, quoted)
         return plan
 
     # ---- section 2 header
     m2 = HeaderMachine(SectionType.TRAJECTORIES)
     err, hdr2 = _feed_header(src, b1[1] + 1, b1[0] + 1, n_rows, m2, name)
     header_quotes += hdr2.count(b'"')
-    _check_quotes(summary, header_quotes, name)
+    _check_quotes(summary, header_quotes, quoted)
     if err is not None:
         plan.deferred_error = err
         return plan
@@ -411,28 +430,19 @@ def _check_supported(lay: SectionLayout, name: str):
         raise NotImplementedError(f"{name}: a section header with fewer than 3 columns is not supported")
 
 
-def _check_quotes(summary, header_quotes: int, name: str):
-    if int(summary.n_quotes) > header_quotes:
-        raise NotImplementedError(f"{name}: quoted fields in data rows are not supported by the CUDA loader yet")
+def _check_quotes(summary, header_quotes: int, quoted: bool):
+    if not quoted and int(summary.n_quotes) > header_quotes:
+        raise _QuotedData()
 
 
-def _raise_device_error(src: _Source, plan: _Plan, key: int, name: str):
+def _raise_device_error(src: _Source, plan: _Plan, key: int, name: str, ws):
     pos, kind = key >> 3, key & 7
     if kind == nat.MS_ERR_KIND_ROW_TOO_LONG:
         raise NotImplementedError(
             f"{name}: a CSV row longer than {nat.MS_MAX_ROW_BYTES} bytes near byte {pos} is not supported"
         )
-    row_index = src.count_terminators_before(pos)
-    # the row: from the terminator before `pos` to the one after it
-    lo = max(0, pos - nat.MS_MAX_ROW_BYTES - 2)
-    window = src.fetch(lo, 2 * nat.MS_MAX_ROW_BYTES + 4)
-    rel = pos - lo
-    start = 0
-    for m in _TERMINATOR.finditer(window, 0, rel):
-        start = m.end()
-    m = _TERMINATOR.search(window, start)
-    line_bytes = window[start : m.end()] if m else window[start:]
-    rows, _ = rows_from_bytes(line_bytes, 1)
+    row_index, start, stop = src.locate_row(ws, pos)
+    rows, _ = rows_from_bytes(src.fetch(start, stop - start), 1)
     num_cols = 0
     for lay, (r0, r1) in zip(plan.layouts, plan.data_rows):
         if lay is not None and r0 <= row_index < r1:
