@@ -367,19 +367,17 @@ __global__ void ms_quote_parity_kernel(const MsTileInfo* __restrict__ tiles, int
 #define RESOLVE_THREADS 1024
 #define RESOLVE_CAND_CAP 64
 
-// terminator ends in [from, to) of the buffer (cooperative, whole block); result valid in thread 0
-__device__ unsigned long long ms_block_count_terms(const uint8_t* __restrict__ src, int64_t n, int64_t from, int64_t to,
+// terminator ends in [from, to) of the buffer, from the masks the scan kernel wrote (so that a
+// quote-aware scan is honoured); cooperative over the whole block
+__device__ unsigned long long ms_block_count_terms(const uint32_t* __restrict__ masks, int64_t from, int64_t to,
                                                    unsigned long long* s_acc) {
     if (threadIdx.x == 0) *s_acc = 0;
     __syncthreads();
     unsigned long long mine = 0;
     const int64_t first_vec = from / 16, last_vec = (to + 15) / 16;
     for (int64_t vi = first_vec + threadIdx.x; vi < last_vec; vi += blockDim.x) {
-        int64_t off = vi * 16;
-        uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
-        MsDelims d = ms_delims16(v);
-        uint32_t next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
-        uint32_t term = ms_term16(d.lf, d.cr, next_lf);
+        const int64_t off = vi * 16;
+        uint32_t term = masks[vi] & 0xffffu;
         // keep bytes in [from, to)
         if (off < from) term &= ~((1u << (from - off)) - 1u);
         if (off + 16 > to) term &= (1u << (to - off)) - 1u;
@@ -391,7 +389,7 @@ __device__ unsigned long long ms_block_count_terms(const uint8_t* __restrict__ s
 }
 
 __global__ void __launch_bounds__(RESOLVE_THREADS)
-    ms_resolve_kernel(const uint8_t* __restrict__ src, int64_t n, const MsTileInfo* __restrict__ tiles,
+    ms_resolve_kernel(const uint32_t* __restrict__ masks, int64_t n, const MsTileInfo* __restrict__ tiles,
                       unsigned long long* __restrict__ term_prefix, int64_t n_tiles, ms_scan_summary* __restrict__ out) {
     const int tid = threadIdx.x;
     __shared__ unsigned long long s_scan[RESOLVE_THREADS / 32];
@@ -534,7 +532,7 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
             row = term_prefix[n_tiles];
         } else {
             const int64_t k = p / MS_TILE_BYTES;
-            unsigned long long c = ms_block_count_terms(src, n, k * (int64_t)MS_TILE_BYTES, p, &s_acc);
+            unsigned long long c = ms_block_count_terms(masks, k * (int64_t)MS_TILE_BYTES, p, &s_acc);
             row = term_prefix[k] + c;
         }
         if (tid == 0) {
@@ -992,7 +990,7 @@ static int ms_scan_impl(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspa
         MS_COUNT_LAUNCH();
         MS_CUDA_CHECK(cudaGetLastError());
     }
-    ms_resolve_kernel<<<1, RESOLVE_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.term_prefix, n_tiles, d_summary);
+    ms_resolve_kernel<<<1, RESOLVE_THREADS, 0, st>>>(v.masks, n_bytes, v.tiles, v.term_prefix, n_tiles, d_summary);
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
