@@ -585,8 +585,10 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 #define PARSE_PAD 16  // bytes staged before and after the region
 #define PARSE_BYTES_SMEM (PARSE_REGION + 2 * PARSE_PAD)
 #define PARSE_NSEG (PARSE_REGION / 16)
-#define PARSE_ROWS_CAP 1024
-#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
+#define PARSE_ROWS_CAP 512
+#define PARSE_CHUNKTAB 1536  // uint32 entries: first byte of every column chunk of every row of a batch
+#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4 + 12 + PARSE_CHUNKTAB * 4)
+#define CHUNK_NONE 0xFFFFFFFFu
 
 struct MsSectionsArg {
     ms_section s[MS_MAX_SECTIONS];
@@ -665,8 +667,8 @@ __device__ __forceinline__ uint32_t ms_digits4(uint32_t t) {
 }
 
 // Parses the field that starts at *pp and advances *pp past its delimiter.
-//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] with <= 19 digits, mantissa <= 2^53 and a
-//                decimal exponent in Clinger's exact range -> one IEEE multiply or divide.
+//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] whose digits fit a 32-bit accumulator and
+//                whose decimal exponent is in Clinger's exact range -> one IEEE multiply or divide.
 //                Digits are converted four at a time (SWAR on one 32-bit word);
 //   anything else: the field's extent is found and the general parser decides (and reports errors).
 // Returns true when the delimiter ended the row.
@@ -687,35 +689,36 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
         c = reg[p];
     } else if (!ms_is_delim(c)) {
-        uint64_t sign = 0;
+        uint32_t sign_hi = 0;
         if (c == '-') {
-            sign = 0x8000000000000000ull;
+            sign_hi = 0x80000000u;
             x = ms_load4(reg, ++p);
         }
-        uint64_t acc = 0;
-        int ndig = 0, nfrac = 0;
-        bool dot = false;
+        // acc holds the digits seen so far; nsig over-counts the digits since the first non-zero
+        // one by at most 3 (whole words are counted), so nsig <= 9 guarantees acc < 10^9 < 2^32
+        uint32_t acc = 0;
+        int ndig = 0, nfrac = 0, nsig = 0;
+        uint32_t dot = 0;  // 0 or 1
         for (;;) {
             const uint32_t t = x ^ 0x30303030u;
             const uint32_t nd = ((t + 0x76767676u) | t) & 0x80808080u;  // bytes that are not digits
-            if (nd == 0) {
-                acc = acc * 10000ull + ms_digits4(t);
-                ndig += 4;
-                nfrac += dot ? 4 : 0;
-                p += 4;
-                x = ms_load4(reg, p);
-                continue;
-            }
-            const int j = (__ffs(nd) - 1) >> 3;  // digits before the first other byte: 0..3
+            const int j = nd ? (__ffs(nd) - 1) >> 3 : 4;                // leading digit bytes: 0..4
             if (j) {
-                acc = acc * (j == 1 ? 10ull : j == 2 ? 100ull : 1000ull) + ms_digits4(t << ((4 - j) << 3));
+                const uint32_t tt = j == 4 ? t : t << ((4 - j) << 3);    // right-align: zeros lead
+                const uint32_t scale = j == 4 ? 10000u : j == 3 ? 1000u : j == 2 ? 100u : 10u;
+                nsig += (acc | tt) ? j : 0;  // before the update: a wrapped accumulator must not hide digits
+                acc = acc * scale + ms_digits4(tt);
                 ndig += j;
                 nfrac += dot ? j : 0;
             }
-            c = (x >> (j << 3)) & 0xffu;
             p += j;
+            if (j == 4) {
+                x = ms_load4(reg, p);
+                continue;
+            }
+            c = (x >> (j << 3)) & 0xffu;
             if (c == '.' && !dot) {
-                dot = true;
+                dot = 1;
                 x = ms_load4(reg, ++p);
                 continue;
             }
@@ -723,7 +726,7 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
         // c = reg[p]: the first byte that is neither a digit nor the (first) decimal point
         int ex = -nfrac;
-        bool ok = ndig > 0 && ndig <= 19;
+        bool ok = ndig > 0 && nsig <= 9;
         if (ok && (c | 0x20u) == 'e') {
             // exponent: at most three digits
             const uint8_t* r = reg + p + 1;
@@ -747,14 +750,10 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
                 ok = false;
             }
         }
-        if (ok && ms_is_delim(c) && (acc == 0 || (acc <= (1ull << 53) && ex >= -22 && ex <= 22))) {
-            if (acc == 0) {
-                bits = sign;
-            } else {
-                double v = (double)acc;
-                v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
-                bits = sign | ms_double_to_bits(v);
-            }
+        if (ok && ms_is_delim(c) && (acc == 0 || (unsigned)(ex + 22) <= 44u)) {
+            double v = (double)acc;  // exact: acc < 2^32
+            if (acc != 0) v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
+            bits = ms_double_to_bits(v) | ((uint64_t)sign_hi << 32);
         } else {
             // general path: [fs, fe) up to the next delimiter
             while (!ms_is_delim(c)) c = reg[++p];
@@ -780,6 +779,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
     uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
     int* const row_start = reinterpret_cast<int*>(smem_raw + PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32);
+    uint32_t* const chunk_tab = reinterpret_cast<uint32_t*>(row_start + PARSE_ROWS_CAP + 4);
     __shared__ int s_warp_terms[PARSE_WARPS];
     __shared__ int s_lt_end, s_next_item;
 
@@ -911,12 +911,45 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
             }
             __syncthreads();
 
-            // ---- B. lanes = rows, lockstep over columns
+            // ---- A5. first byte of every column chunk of every row: one popcount walk per row over
+            // its comma masks (a row group is split into column chunks to keep all warps busy)
             const int groups = (nrows + 31) >> 5;
-            int nchunks = (3 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 3 items per warp
-            nchunks = max(1, min(nchunks, ncols / 4));
+            int nchunks = (4 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 4 items per warp
+            nchunks = max(1, min(nchunks, ncols / 2));
+            if (nchunks > 1) nchunks = min(nchunks, PARSE_CHUNKTAB / nrows + 1);
             const int cs = (ncols + nchunks - 1) / nchunks;  // columns per chunk
             nchunks = (ncols + cs - 1) / cs;
+            if (nchunks > 1) {
+                for (int g = warp; g < groups; g += PARSE_WARPS) {
+                    const int r = (g << 5) + lane;
+                    if (r >= nrows) continue;
+                    const int row_end = row_start[r + 1];  // one past the row's terminator
+                    int p = row_start[r];
+                    int seg = p >> 4;
+                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
+                    int seen = 0, k = 1;
+                    while (k < nchunks) {
+                        const int target = k * cs - seen;  // commas to pass, counted from this segment
+                        if (__popc(m) >= target) {
+                            uint32_t mm = m;
+                            for (int i = 1; i < target; i++) mm &= mm - 1u;
+                            const int pos = (seg << 4) + __ffs(mm);  // one past the comma before column k*cs
+                            if (pos >= row_end) break;               // that comma belongs to a later row: short row
+                            chunk_tab[(k - 1) * nrows + r] = (uint32_t)pos;
+                            k++;
+                        } else {
+                            seen += __popc(m);
+                            seg++;
+                            if ((seg << 4) >= row_end) break;
+                            m = cmask[seg];
+                        }
+                    }
+                    for (; k < nchunks; k++) chunk_tab[(k - 1) * nrows + r] = CHUNK_NONE;  // the row ends earlier
+                }
+                __syncthreads();
+            }
+
+            // ---- B. lanes = rows, lockstep over columns
             const int items = groups * nchunks;
             for (;;) {
                 // warps take (row group, column chunk) items from a shared counter
@@ -924,40 +957,20 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
                 if (lane == 0) item = atomicAdd(&s_next_item, 1);
                 item = __shfl_sync(0xffffffffu, item, 0);
                 if (item >= items) break;
-                const int g = item / nchunks, k = item - g * nchunks;
+                const int k = item / groups, g = item - k * groups;  // chunk-major: long columns spread over warps
                 const int r = (g << 5) + lane;
                 if (r < nrows) {
-                const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
-                int p = row_start[r];
-                bool done = false;
-                if (c_lo > 0) {
-                    // first byte of column c_lo = one past the c_lo-th comma of the row, if the row has it
-                    const int row_end = row_start[r + 1];  // one past the row's terminator
-                    int seg = p >> 4;
-                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
-                    int need = c_lo;
-                    int cnt = __popc(m);
-                    while (cnt < need && (seg << 4) < row_end) {
-                        need -= cnt;
-                        m = cmask[++seg];
-                        cnt = __popc(m);
+                    const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
+                    const uint32_t p0 = k == 0 ? (uint32_t)row_start[r] : chunk_tab[(k - 1) * nrows + r];
+                    bool done = p0 == CHUNK_NONE;
+                    int p = (int)p0;
+                    double* out = out_base + (int64_t)(c_lo - 2) * out_stride + (out_row0 + ba + r);
+                    for (int c = c_lo; c < c_hi; c++, out += out_stride) {
+                        uint64_t bits = MS_NAN_BITS;
+                        if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
+                        const int ch = c - 2;
+                        if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
                     }
-                    if (cnt < need) {
-                        done = true;
-                    } else {
-                        for (int i = 1; i < need; i++) m &= m - 1u;
-                        p = (seg << 4) + __ffs(m);  // position after that comma
-                        // the comma must belong to this row (a terminator may come first)
-                        if (p > row_end - 1) done = true;
-                    }
-                }
-                double* out = out_base + (int64_t)(c_lo - 2) * out_stride + (out_row0 + ba + r);
-                for (int c = c_lo; c < c_hi; c++, out += out_stride) {
-                    uint64_t bits = MS_NAN_BITS;
-                    if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
-                    const int ch = c - 2;
-                    if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
-                }
                 }
             }
             __syncthreads();  // row_start is reused by the next batch
