@@ -571,8 +571,9 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 //      divergence), walking their row left to right and finding each field's end while parsing
 //      it, and store 32 consecutive doubles of one channel (coalesced 256-byte stores, no
 //      transpose staging).  The ignored tail of a row (fields beyond num_cols) is never touched.
-//      To keep all warps busy a row group is split into column chunks; a chunk locates its first
-//      column with a popcount walk over the row's comma masks.
+//      To keep all warps busy a row group is split into column chunks handed out from a shared
+//      counter; a chunk locates its first column with a popcount walk over the row's comma masks
+//      (precomputing those starts in a separate step was measured slower: it serialises on a barrier).
 //
 // Rows are processed in batches of PARSE_ROWS_CAP per section, so pathological inputs
 // (thousands of tiny rows in a tile) only cost more rounds.
@@ -586,71 +587,70 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 #define PARSE_BYTES_SMEM (PARSE_REGION + 2 * PARSE_PAD)
 #define PARSE_NSEG (PARSE_REGION / 16)
 #define PARSE_ROWS_CAP 512
-#define PARSE_CHUNKTAB 1536  // uint32 entries: first byte of every column chunk of every row of a batch
-#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4 + 12 + PARSE_CHUNKTAB * 4)
-#define CHUNK_NONE 0xFFFFFFFFu
+#define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
 
 struct MsSectionsArg {
     ms_section s[MS_MAX_SECTIONS];
     int n;
 };
 
-struct MsParsed {
-    uint64_t bits;
-    int status;
-};
-// General (exact for every input) parser, out of line: the inline path below handles what Vicon
-// exports actually contain.
-__device__ __noinline__ MsParsed ms_parse_field_call(const uint8_t* s, const uint8_t* e) {
-    MsParsed r;
-    r.bits = MS_NAN_BITS;
-    r.status = ms_parse_field(s, e, &r.bits);
-    return r;
-}
-
 __device__ __forceinline__ bool ms_is_delim(unsigned c) { return c == ',' || c == '\n' || c == '\r'; }
 
-// A field that starts with '"' (excel dialect of csv.reader, load_csv.py:30): the content runs to
-// the closing quote, "" is a literal quote, and - csv is not strict - text after the closing
-// quote is appended up to the next delimiter.  *pp: the opening quote on entry, the field's
-// delimiter on return.  An empty content is an empty field (None -> NaN in the reference).
+// Everything the inline path of ms_parse_next does not take: finds the extent of the field that
+// starts at reg[fs], parses it with the general parser and records an error.  Handles fields that
+// start with '"' (excel dialect of csv.reader, load_csv.py:30): the content runs to the closing
+// quote, "" is a literal quote and - csv is not strict - text after the closing quote is appended
+// up to the next delimiter; an empty content is an empty field (None -> NaN in the reference).
+// Returns the bits; *pend = offset of the delimiter that ends the field.
 #define MS_QUOTED_MAX 64
-__device__ __noinline__ MsParsed ms_parse_quoted_call(const uint8_t* __restrict__ reg, int* pp) {
-    uint8_t buf[MS_QUOTED_MAX];
-    int n = 0, q = *pp + 1;
-    bool too_long = false;
-    for (;;) {
-        unsigned c = reg[q];
-        if (q >= PARSE_REGION) break;  // unbalanced quote: stop at the end of the staged bytes
-        if (c == '"') {
-            if (reg[q + 1] != '"') {
+__device__ __noinline__ uint64_t ms_parse_slow_call(const uint8_t* __restrict__ reg, int fs, int* pend,
+                                                    unsigned long long* status, int64_t t0) {
+    uint64_t bits = MS_NAN_BITS;
+    int st = MS_PARSE_OK;
+    int q = fs;
+    if (reg[fs] == '"') {
+        uint8_t buf[MS_QUOTED_MAX];
+        int n = 0;
+        bool too_long = false;
+        q = fs + 1;
+        for (;;) {
+            if (q >= PARSE_REGION) break;  // unbalanced quote: stop at the end of the staged bytes
+            unsigned c = reg[q];
+            if (c == '"') {
+                if (reg[q + 1] != '"') {
+                    q++;
+                    break;
+                }
                 q++;
-                break;
             }
+            if (n < MS_QUOTED_MAX)
+                buf[n++] = (uint8_t)c;
+            else
+                too_long = true;
             q++;
         }
-        if (n < MS_QUOTED_MAX)
-            buf[n++] = (uint8_t)c;
-        else
-            too_long = true;
-        q++;
+        while (q < PARSE_REGION && !ms_is_delim(reg[q])) {
+            if (n < MS_QUOTED_MAX)
+                buf[n++] = reg[q];
+            else
+                too_long = true;
+            q++;
+        }
+        if (too_long)
+            st = MS_PARSE_BAD;
+        else if (n > 0)
+            st = ms_parse_field(buf, buf + n, &bits);
+    } else {
+        while (!ms_is_delim(reg[q])) q++;
+        st = ms_parse_field(reg + fs, reg + q, &bits);
     }
-    while (q < PARSE_REGION && !ms_is_delim(reg[q])) {
-        if (n < MS_QUOTED_MAX)
-            buf[n++] = reg[q];
-        else
-            too_long = true;
-        q++;
+    if (st != MS_PARSE_OK) {
+        bits = MS_NAN_BITS;
+        atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
+                              (st == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
     }
-    *pp = q;
-    MsParsed r;
-    r.bits = MS_NAN_BITS;
-    r.status = MS_PARSE_OK;
-    if (too_long)
-        r.status = MS_PARSE_BAD;
-    else if (n > 0)
-        r.status = ms_parse_field(buf, buf + n, &r.bits);
-    return r;
+    *pend = q;
+    return bits;
 }
 
 // Four bytes at an arbitrary offset of the staged region (little endian): two aligned word
@@ -667,10 +667,11 @@ __device__ __forceinline__ uint32_t ms_digits4(uint32_t t) {
 }
 
 // Parses the field that starts at *pp and advances *pp past its delimiter.
-//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] whose digits fit a 32-bit accumulator and
-//                whose decimal exponent is in Clinger's exact range -> one IEEE multiply or divide.
-//                Digits are converted four at a time (SWAR on one 32-bit word);
-//   anything else: the field's extent is found and the general parser decides (and reports errors).
+//   inline path: [-]digits[.digits][(e|E)[+-]d{1,3}] with <= 19 digits, mantissa <= 2^53 and a
+//                decimal exponent in Clinger's exact range -> one IEEE multiply or divide.
+//                Digits are converted four at a time (SWAR on one 32-bit word).  (A 32-bit
+//                accumulator variant was measured 3 % slower: more selects than it saves.)
+//   anything else, quoted fields included: ms_parse_slow_call decides (and reports errors).
 // Returns true when the delimiter ended the row.
 __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, int* pp, uint64_t* bits_out,
                                               unsigned long long* status, int64_t t0) {
@@ -679,46 +680,36 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
     uint32_t x = ms_load4(reg, p);
     unsigned c = x & 0xffu;
     uint64_t bits = MS_NAN_BITS;
-    if (c == '"') {
-        MsParsed pr = ms_parse_quoted_call(reg, &p);
-        bits = pr.bits;
-        if (pr.status != MS_PARSE_OK) {
-            bits = MS_NAN_BITS;
-            atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
-                                  (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
-        }
-        c = reg[p];
-    } else if (!ms_is_delim(c)) {
-        uint32_t sign_hi = 0;
+    if (!ms_is_delim(c)) {
+        uint64_t sign = 0;
         if (c == '-') {
-            sign_hi = 0x80000000u;
+            sign = 0x8000000000000000ull;
             x = ms_load4(reg, ++p);
         }
-        // acc holds the digits seen so far; nsig over-counts the digits since the first non-zero
-        // one by at most 3 (whole words are counted), so nsig <= 9 guarantees acc < 10^9 < 2^32
-        uint32_t acc = 0;
-        int ndig = 0, nfrac = 0, nsig = 0;
-        uint32_t dot = 0;  // 0 or 1
+        uint64_t acc = 0;
+        int ndig = 0, nfrac = 0;
+        bool dot = false;
         for (;;) {
             const uint32_t t = x ^ 0x30303030u;
             const uint32_t nd = ((t + 0x76767676u) | t) & 0x80808080u;  // bytes that are not digits
-            const int j = nd ? (__ffs(nd) - 1) >> 3 : 4;                // leading digit bytes: 0..4
-            if (j) {
-                const uint32_t tt = j == 4 ? t : t << ((4 - j) << 3);    // right-align: zeros lead
-                const uint32_t scale = j == 4 ? 10000u : j == 3 ? 1000u : j == 2 ? 100u : 10u;
-                nsig += (acc | tt) ? j : 0;  // before the update: a wrapped accumulator must not hide digits
-                acc = acc * scale + ms_digits4(tt);
-                ndig += j;
-                nfrac += dot ? j : 0;
-            }
-            p += j;
-            if (j == 4) {
+            if (nd == 0) {
+                acc = acc * 10000ull + ms_digits4(t);
+                ndig += 4;
+                nfrac += dot ? 4 : 0;
+                p += 4;
                 x = ms_load4(reg, p);
                 continue;
             }
+            const int j = (__ffs(nd) - 1) >> 3;  // digits before the first other byte: 0..3
+            if (j) {
+                acc = acc * (j == 1 ? 10ull : j == 2 ? 100ull : 1000ull) + ms_digits4(t << ((4 - j) << 3));
+                ndig += j;
+                nfrac += dot ? j : 0;
+            }
             c = (x >> (j << 3)) & 0xffu;
+            p += j;
             if (c == '.' && !dot) {
-                dot = 1;
+                dot = true;
                 x = ms_load4(reg, ++p);
                 continue;
             }
@@ -726,7 +717,7 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
         // c = reg[p]: the first byte that is neither a digit nor the (first) decimal point
         int ex = -nfrac;
-        bool ok = ndig > 0 && nsig <= 9;
+        bool ok = ndig > 0 && ndig <= 19;
         if (ok && (c | 0x20u) == 'e') {
             // exponent: at most three digits
             const uint8_t* r = reg + p + 1;
@@ -750,26 +741,25 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
                 ok = false;
             }
         }
-        if (ok && ms_is_delim(c) && (acc == 0 || (unsigned)(ex + 22) <= 44u)) {
-            double v = (double)acc;  // exact: acc < 2^32
-            if (acc != 0) v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
-            bits = ms_double_to_bits(v) | ((uint64_t)sign_hi << 32);
-        } else {
-            // general path: [fs, fe) up to the next delimiter
-            while (!ms_is_delim(c)) c = reg[++p];
-            MsParsed pr = ms_parse_field_call(reg + fs, reg + p);
-            bits = pr.bits;
-            if (pr.status != MS_PARSE_OK) {
-                bits = MS_NAN_BITS;
-                atomicMin(status, ((unsigned long long)(t0 + fs) << 3) |
-                                      (pr.status == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+        if (ok && ms_is_delim(c) && (acc == 0 || (acc <= (1ull << 53) && ex >= -22 && ex <= 22))) {
+            if (acc == 0) {
+                bits = sign;
+            } else {
+                double v = (double)acc;
+                v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
+                bits = sign | ms_double_to_bits(v);
             }
+        } else {
+            // everything else (quoted fields too): out of line
+            bits = ms_parse_slow_call(reg, fs, &p, status, t0);
+            c = reg[p];
         }
     }
     *bits_out = bits;
     *pp = p + 1;
     return c != ',';
 }
+
 
 __global__ void __launch_bounds__(PARSE_THREADS, 3)
     ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
@@ -779,7 +769,6 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     uint8_t* const reg = smem_raw + PARSE_PAD;  // reg[i] = src[t0 + i]
     uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
     int* const row_start = reinterpret_cast<int*>(smem_raw + PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32);
-    uint32_t* const chunk_tab = reinterpret_cast<uint32_t*>(row_start + PARSE_ROWS_CAP + 4);
     __shared__ int s_warp_terms[PARSE_WARPS];
     __shared__ int s_lt_end, s_next_item;
 
@@ -911,45 +900,12 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
             }
             __syncthreads();
 
-            // ---- A5. first byte of every column chunk of every row: one popcount walk per row over
-            // its comma masks (a row group is split into column chunks to keep all warps busy)
+            // ---- B. lanes = rows, lockstep over columns
             const int groups = (nrows + 31) >> 5;
-            int nchunks = (4 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 4 items per warp
-            nchunks = max(1, min(nchunks, ncols / 2));
-            if (nchunks > 1) nchunks = min(nchunks, PARSE_CHUNKTAB / nrows + 1);
+            int nchunks = (3 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 3 items per warp
+            nchunks = max(1, min(nchunks, ncols / 4));
             const int cs = (ncols + nchunks - 1) / nchunks;  // columns per chunk
             nchunks = (ncols + cs - 1) / cs;
-            if (nchunks > 1) {
-                for (int g = warp; g < groups; g += PARSE_WARPS) {
-                    const int r = (g << 5) + lane;
-                    if (r >= nrows) continue;
-                    const int row_end = row_start[r + 1];  // one past the row's terminator
-                    int p = row_start[r];
-                    int seg = p >> 4;
-                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
-                    int seen = 0, k = 1;
-                    while (k < nchunks) {
-                        const int target = k * cs - seen;  // commas to pass, counted from this segment
-                        if (__popc(m) >= target) {
-                            uint32_t mm = m;
-                            for (int i = 1; i < target; i++) mm &= mm - 1u;
-                            const int pos = (seg << 4) + __ffs(mm);  // one past the comma before column k*cs
-                            if (pos >= row_end) break;               // that comma belongs to a later row: short row
-                            chunk_tab[(k - 1) * nrows + r] = (uint32_t)pos;
-                            k++;
-                        } else {
-                            seen += __popc(m);
-                            seg++;
-                            if ((seg << 4) >= row_end) break;
-                            m = cmask[seg];
-                        }
-                    }
-                    for (; k < nchunks; k++) chunk_tab[(k - 1) * nrows + r] = CHUNK_NONE;  // the row ends earlier
-                }
-                __syncthreads();
-            }
-
-            // ---- B. lanes = rows, lockstep over columns
             const int items = groups * nchunks;
             for (;;) {
                 // warps take (row group, column chunk) items from a shared counter
@@ -957,20 +913,40 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
                 if (lane == 0) item = atomicAdd(&s_next_item, 1);
                 item = __shfl_sync(0xffffffffu, item, 0);
                 if (item >= items) break;
-                const int k = item / groups, g = item - k * groups;  // chunk-major: long columns spread over warps
+                const int g = item / nchunks, k = item - g * nchunks;
                 const int r = (g << 5) + lane;
                 if (r < nrows) {
-                    const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
-                    const uint32_t p0 = k == 0 ? (uint32_t)row_start[r] : chunk_tab[(k - 1) * nrows + r];
-                    bool done = p0 == CHUNK_NONE;
-                    int p = (int)p0;
-                    double* out = out_base + (int64_t)(c_lo - 2) * out_stride + (out_row0 + ba + r);
-                    for (int c = c_lo; c < c_hi; c++, out += out_stride) {
-                        uint64_t bits = MS_NAN_BITS;
-                        if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
-                        const int ch = c - 2;
-                        if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
+                int p = row_start[r];
+                bool done = false;
+                if (c_lo > 0) {
+                    // first byte of column c_lo = one past the c_lo-th comma of the row, if the row has it
+                    const int row_end = row_start[r + 1];  // one past the row's terminator
+                    int seg = p >> 4;
+                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
+                    int need = c_lo;
+                    int cnt = __popc(m);
+                    while (cnt < need && (seg << 4) < row_end) {
+                        need -= cnt;
+                        m = cmask[++seg];
+                        cnt = __popc(m);
                     }
+                    if (cnt < need) {
+                        done = true;
+                    } else {
+                        for (int i = 1; i < need; i++) m &= m - 1u;
+                        p = (seg << 4) + __ffs(m);  // position after that comma
+                        // the comma must belong to this row (a terminator may come first)
+                        if (p > row_end - 1) done = true;
+                    }
+                }
+                double* out = out_base + (int64_t)(c_lo - 2) * out_stride + (out_row0 + ba + r);
+                for (int c = c_lo; c < c_hi; c++, out += out_stride) {
+                    uint64_t bits = MS_NAN_BITS;
+                    if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
+                    const int ch = c - 2;
+                    if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                }
                 }
             }
             __syncthreads();  // row_start is reused by the next batch
