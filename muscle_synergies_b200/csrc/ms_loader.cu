@@ -156,12 +156,20 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t*
     int w_first = -1, w_last = -1;  // meaningful in the lane that sees them; reduced at the end
     uint32_t w_nb_head = 0;
 
+    // software pipeline: the vector of iteration it+1 is in flight while iteration it is classified
+    // (beyond the end: commas - blank, not a terminator)
+    const int64_t span0 = t0 + warp * SCAN_SPAN;
+    uint4 vcur = make_uint4(0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu);
+    if (span0 < n) vcur = ms_load16(src, span0 + lane * 16, n, 0x2c2c2c2cu);
     for (int it = 0; it < SCAN_ITERS; it++) {
         const int rel = warp * SCAN_SPAN + it * 512 + lane * 16;
         const int64_t off = t0 + rel;
-        if (t0 + warp * SCAN_SPAN + it * 512 >= n) break;  // warp-uniform: nothing left in this span
-        // beyond the end: commas (blank, not a terminator)
-        const uint4 v = ms_load16(src, off, n, 0x2c2c2c2cu);
+        if (span0 + it * 512 >= n) break;  // warp-uniform: nothing left in this span
+        const bool has_next = (it + 1 < SCAN_ITERS) && (span0 + (it + 1) * 512 < n);  // warp-uniform
+        uint4 vnext = make_uint4(0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu);
+        if (has_next) vnext = ms_load16(src, off + 512, n, 0x2c2c2c2cu);
+        const uint4 v = vcur;
+        vcur = vnext;
         const uint32_t w[4] = {v.x, v.y, v.z, v.w};
         uint32_t lf16 = 0, cr16 = 0, comma16 = 0, gt16 = 0, hib = 0, quote16 = 0;
 #pragma unroll
@@ -205,7 +213,18 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t*
         }
         // byte after this vector: first byte of the next lane's vector
         uint32_t next_lf = __shfl_down_sync(0xffffffffu, lf16 & 1u, 1);
-        if (lane == 31) next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;  // (a quoted "\r\n" never ends a vector pair-split: both bytes are masked)
+        {
+            // lane 31: the byte after its vector is lane 0's first byte of the next iteration (already
+            // loaded); at the end of the span it is read directly.  Raw byte: a '\r' that survives the
+            // quote filter is outside quotes, and so is the byte after it.
+            const uint32_t first_next = __shfl_sync(0xffffffffu, vnext.x & 0xffu, 0);
+            if (lane == 31) {
+                if (has_next)
+                    next_lf = first_next == '\n';
+                else
+                    next_lf = (off + 16 < n) ? (uint32_t)(src[off + 16] == '\n') : 0u;
+            }
+        }
         const uint32_t term = ms_term16(lf16, cr16, next_lf);
         if (off < n) {
             uint32_t cm = comma16;
@@ -784,17 +803,25 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
         if (row_hi >= secs.s[i].row_begin && row_lo < secs.s[i].row_end) any = true;
     if (!any) return;
 
-    // ---- A1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'
+    // ---- A1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'.
+    // Asynchronous 16-byte copies (cp.async, LDGSTS): they stay in flight while the masks are
+    // fetched and scanned below; the bytes are first needed for the ownership test.
     for (int i = tid; i < PARSE_BYTES_SMEM / 16; i += PARSE_THREADS) {
-        int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
-        uint4 v;
-        if (off < 0)
-            v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-        else
-            v = ms_load16(src, off, n, 0x0a0a0a0au);
-        *reinterpret_cast<uint4*>(smem_raw + i * 16) = v;
+        const int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
+        uint8_t* dst = smem_raw + i * 16;
+        if (off >= 0 && off + 16 <= n) {
+            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
+            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(src + off) : "memory");
+        } else {
+            uint4 v;
+            if (off < 0)
+                v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+            else
+                v = ms_load16(src, off, n, 0x0a0a0a0au);
+            *reinterpret_cast<uint4*>(dst) = v;
+        }
     }
-    __syncthreads();
+    asm volatile("cp.async.commit_group;\n" ::: "memory");
 
     // ---- A2. delimiter masks of my chunk: classified once, by ms_scan_kernel
     const int c0 = tid * PARSE_CHUNK;
@@ -851,6 +878,10 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     }
     const int lt0 = before + inc - my_terms;  // terminators before my chunk
     if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
+    __syncthreads();
+
+    // the staged bytes are needed from here on
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
     __syncthreads();
 
     // ---- ownership: rows that START in [t0, t0 + tile_len)

@@ -86,9 +86,11 @@ def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments
     dev = left_fz.device
     want = num_segments if num_segments > 0 else max(1, n)
     work = torch.empty(int(lib.ms_transitions_workspace_bytes(n)), dtype=torch.uint8, device=dev)
-    out = torch.empty(want, dtype=torch.int64, device=dev)
-    loaded = torch.empty(want, dtype=torch.int32, device=dev)
-    found = torch.zeros(1, dtype=torch.int32, device=dev)
+    # one result buffer -> one device->host copy: [indices (int64) | loaded flags, count (int32)]
+    res = torch.empty(want + (want + 2 + 1) // 2, dtype=torch.int64, device=dev)
+    out = res[:want]
+    tail = res[want:].view(torch.int32)
+    loaded, found = tail[:want], tail[want : want + 1]
     stream = torch.cuda.current_stream(dev)
     nat.check(
         lib.ms_find_transitions(
@@ -97,16 +99,18 @@ def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments
         ),
         "ms_find_transitions",
     )
-    k = int(found.item())
+    host = res.cpu()
+    k = int(host[want:].view(torch.int32)[want].item())
     if num_segments > 0 and k < num_segments:
         legs = 1 if k % 2 == 0 else 2
         raise ValueError(
             f"no phase found with {min_phase_size} adjacent measurements with {legs} leg(s) with a nonzero reaction"
             f" (found {k} of {num_segments} transitions)"
         )
-    idx = out[:k].tolist()
+    idx = host[:k].tolist()
+    loaded_host = host[want:].view(torch.int32)[:k].tolist()
     if with_loaded:
-        return idx, loaded[:k].tolist()
+        return idx, loaded_host
     return idx
 
 
@@ -262,7 +266,7 @@ def cut_windows(device: DeviceData, index_slices: Sequence[slice]):
     for ln in lens:
         offsets.append(offsets[-1] + ln * n_ch)
     dev = src.device
-    meta = torch.tensor([starts, stops, offsets[:-1]], dtype=torch.int64).to(dev, non_blocking=False)
+    meta = torch.tensor([starts, stops, offsets[:-1]], dtype=torch.int64).pin_memory().to(dev, non_blocking=True)
     out = torch.empty(max(1, offsets[-1]), dtype=torch.float64, device=dev)
     stream = torch.cuda.current_stream(dev)
     if index_slices and n_ch:

@@ -160,6 +160,7 @@ class _SectionFrameTracker:
 
     def __init__(self, sampling_freq: SamplingFreq):
         self._sampling_freq = sampling_freq
+        self._num_subframes = None  # computed (and its integrality asserted) on first use, like the reference
 
     @property
     def num_frames(self) -> int:
@@ -167,7 +168,9 @@ class _SectionFrameTracker:
 
     @property
     def num_subframes(self) -> int:
-        return self._sampling_freq.num_subframes
+        if self._num_subframes is None:
+            self._num_subframes = self._sampling_freq.num_subframes
+        return self._num_subframes
 
     @property
     def sampling_frequency(self) -> int:
