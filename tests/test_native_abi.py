@@ -57,11 +57,11 @@ def test_no_cpu_fallback_without_gpu():
 
 
 def test_product_does_not_import_oracle():
+    """The oracle is test infrastructure: nothing in the product may import, link or call it."""
     pkg = os.path.join(ROOT, "muscle_synergies_b200")
     for base, _dirs, files in os.walk(pkg):
         for f in files:
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 text = open(os.path.join(base, f), errors="ignore").read()
-                assert "oracle" not in text.replace("oracle/", "").lower() or f == "__init__.py" or \
-                    "import oracle" not in text and "from oracle" not in text, f
                 assert "import oracle" not in text and "from oracle" not in text, f
+                assert "vicon_oracle" not in text and "libvicon_oracle" not in text, f
