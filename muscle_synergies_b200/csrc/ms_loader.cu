@@ -606,6 +606,7 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 #define PARSE_BYTES_SMEM (PARSE_REGION + 2 * PARSE_PAD)
 #define PARSE_NSEG (PARSE_REGION / 16)
 #define PARSE_ROWS_CAP 512
+#define PARSE_MAX_CHUNKS 32
 #define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
 
 struct MsSectionsArg {
@@ -736,7 +737,7 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
         // c = reg[p]: the first byte that is neither a digit nor the (first) decimal point
         int ex = -nfrac;
-        bool ok = ndig > 0 && ndig <= 19;
+        bool ok = (unsigned)(ndig - 1) <= 14u;  // 1..15 digits: acc < 10^15 < 2^53
         if (ok && (c | 0x20u) == 'e') {
             // exponent: at most three digits
             const uint8_t* r = reg + p + 1;
@@ -760,14 +761,16 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
                 ok = false;
             }
         }
-        if (ok && ms_is_delim(c) && (acc == 0 || (acc <= (1ull << 53) && ex >= -22 && ex <= 22))) {
-            if (acc == 0) {
-                bits = sign;
+        if (ok && ms_is_delim(c) && (unsigned)(ex + 22) <= 44u) {
+            double v;
+            if (ex >= 0) {
+                v = (double)acc * ms_pow10_double[ex];
+            } else if ((acc >> 32) == 0) {
+                v = ms_div_pow10_u32((uint32_t)acc, -ex);  // exact, division-free (exhaustively verified)
             } else {
-                double v = (double)acc;
-                v = ex < 0 ? v / ms_pow10_double[-ex] : v * ms_pow10_double[ex];
-                bits = sign | ms_double_to_bits(v);
+                v = (double)acc / ms_pow10_double[-ex];
             }
+            bits = sign | ms_double_to_bits(v);
         } else {
             // everything else (quoted fields too): out of line
             bits = ms_parse_slow_call(reg, fs, &p, status, t0);
@@ -789,7 +792,8 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + PARSE_BYTES_SMEM);  // commas per 16-byte segment
     int* const row_start = reinterpret_cast<int*>(smem_raw + PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32);
     __shared__ int s_warp_terms[PARSE_WARPS];
-    __shared__ int s_lt_end, s_next_item;
+    __shared__ int s_lt_end, s_next_item, s_nchunks;
+    __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];  // column chunk boundaries (descending)
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int64_t tile = blockIdx.x;
@@ -915,6 +919,27 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
             if (tid == 0) {
                 s_next_item = 0;
                 if (starts_at_t0 && ba == 0) row_start[0] = 0;
+                // Column chunks of DECREASING width, handed out widest first (chunk-major), so that the
+                // last items a warp can draw are small and the warps finish the tile together (uniform
+                // chunks left ~30 % of the warps idle at the end of every tile).  The widest chunk is
+                // the END of the row: in a Devices row those are the EMG columns, the longest fields.
+                // s_chunk_col is descending: chunk j covers columns [s_chunk_col[j+1], s_chunk_col[j]).
+                const int groups_ = (nrows + 31) >> 5;
+                const int ideal = (groups_ * ncols + PARSE_WARPS - 1) / PARSE_WARPS;  // column-groups per warp
+#ifndef MS_EXP_UNUM
+#define MS_EXP_UNUM 3
+#define MS_EXP_UDEN 4
+#endif
+                const int u = max(2, (ideal * MS_EXP_UNUM + MS_EXP_UDEN - 1) / MS_EXP_UDEN);
+                int k = 0, col = 0;
+                while (col < ncols && k < PARSE_MAX_CHUNKS - 1) {
+                    s_chunk_col[k++] = ncols - col;
+                    const int rest = ncols - col;
+                    col += max(1, min(u, (rest + 2) / 3));
+                }
+                if (col < ncols) s_chunk_col[k++] = ncols - col;  // cap reached: one last chunk takes the rest
+                s_chunk_col[k] = 0;
+                s_nchunks = k;
             }
             {
                 int lt = lt0;
@@ -933,10 +958,7 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
 
             // ---- B. lanes = rows, lockstep over columns
             const int groups = (nrows + 31) >> 5;
-            int nchunks = (3 * PARSE_WARPS + groups - 1) / groups;  // aim at >= 3 items per warp
-            nchunks = max(1, min(nchunks, ncols / 4));
-            const int cs = (ncols + nchunks - 1) / nchunks;  // columns per chunk
-            nchunks = (ncols + cs - 1) / cs;
+            const int nchunks = s_nchunks;
             const int items = groups * nchunks;
             for (;;) {
                 // warps take (row group, column chunk) items from a shared counter
@@ -944,10 +966,10 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
                 if (lane == 0) item = atomicAdd(&s_next_item, 1);
                 item = __shfl_sync(0xffffffffu, item, 0);
                 if (item >= items) break;
-                const int g = item / nchunks, k = item - g * nchunks;
+                const int k = item / groups, g = item - k * groups;  // chunk-major: wide chunks first
                 const int r = (g << 5) + lane;
                 if (r < nrows) {
-                const int c_lo = k * cs, c_hi = min(ncols, c_lo + cs);
+                const int c_lo = s_chunk_col[k + 1], c_hi = s_chunk_col[k];
                 int p = row_start[r];
                 bool done = false;
                 if (c_lo > 0) {

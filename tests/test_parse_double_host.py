@@ -112,3 +112,16 @@ def test_grammar_fuzz(harness):
     for _ in range(150_000):
         s = "".join(rnd.choice(alphabet) for _ in range(rnd.randrange(1, 10)))
         agree(harness, s.encode())
+
+
+def test_division_free_clinger_step_is_exact_exhaustively(tmp_path):
+    """a / 10^k via (a*y, fma, fma) with y = RN(1/10^k) equals the IEEE quotient for EVERY integer
+    a < 2^26 and k <= 22 (tests/native/div_check.c; the same program was run once for a < 2^32)."""
+    import subprocess
+
+    exe = tmp_path / "div_check"
+    subprocess.check_call(["gcc", "-O2", "-mfma", "-fopenmp", os.path.join(ROOT, "tests", "native", "div_check.c"),
+                           "-o", str(exe), "-lm"])
+    out = subprocess.run([str(exe)], capture_output=True, text=True)
+    assert out.returncode == 0, out.stdout[-400:]
+    assert "TOTAL one-correction 0 two-correction 0" in out.stdout
