@@ -239,6 +239,8 @@ class _SectionFrameTracker:
 
 
 class ForcesEMGFrameTracker(_SectionFrameTracker):
+    _final_index = None
+
     @property
     def sampling_frequency(self) -> int:
         return self._sampling_freq.freq_forces_emg
@@ -252,7 +254,9 @@ class ForcesEMGFrameTracker(_SectionFrameTracker):
 
     @property
     def final_index(self) -> int:
-        return self.num_frames * self.num_subframes - 1
+        if self._final_index is None:
+            self._final_index = self.num_frames * self.num_subframes - 1
+        return self._final_index
 
 
 class TrajFrameTracker(_SectionFrameTracker):
