@@ -960,13 +960,14 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
             const int groups = (nrows + 31) >> 5;
             const int nchunks = s_nchunks;
             const int items = groups * nchunks;
+            const uint32_t inv_groups = (65536u + groups - 1) / groups;  // item / groups by multiply-shift (items < 2^9)
             for (;;) {
                 // warps take (row group, column chunk) items from a shared counter
                 int item = 0;
                 if (lane == 0) item = atomicAdd(&s_next_item, 1);
                 item = __shfl_sync(0xffffffffu, item, 0);
                 if (item >= items) break;
-                const int k = item / groups, g = item - k * groups;  // chunk-major: wide chunks first
+                const int k = (int)(((uint32_t)item * inv_groups) >> 16), g = item - k * groups;  // chunk-major: wide chunks first
                 const int r = (g << 5) + lane;
                 if (r < nrows) {
                 const int c_lo = s_chunk_col[k + 1], c_hi = s_chunk_col[k];

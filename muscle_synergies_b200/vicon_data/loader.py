@@ -260,26 +260,36 @@ class ViconLoader:
         data.blocks = [b for b in blocks if b is not None]  # the per-section HBM blocks (extension)
         return data
 
-    def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2):
+    def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2, return_exceptions: bool = False):
         """Pipelined batch load: yields one ViconNexusData per source, in order.
 
-        sources: pinned uint8 CPU tensors (or anything load_bytes accepts; non-pinned inputs
-        are staged through one pinned buffer and lose the overlap).  While file i is scanned
-        and parsed on the compute stream, file i+1 is copied host->device on a copy stream
-        and the arrays of file i-1 travel device->host on a third stream (PCIe is full
-        duplex).  With to_host the section blocks are copied into a ring of `host_slots`
-        pinned buffers: the host arrays of file i stay valid until file i + host_slots is
-        yielded.  Errors in a file are raised when that file is reached."""
+        sources: an iterable of pinned uint8 CPU tensors (or anything load_bytes accepts;
+        non-pinned inputs are staged through a fresh pinned buffer).  While file i is scanned and
+        parsed on the compute stream, file i+1 is copied host->device on a copy stream and the
+        arrays of file i-1 travel device->host on a third stream (PCIe is full duplex).  With
+        to_host the section blocks are copied into a ring of `host_slots` pinned buffers: the host
+        arrays of file i stay valid until file i + host_slots is yielded.  An error in a file is
+        raised when that file is reached - or, with return_exceptions, yielded in its place so
+        that the rest of the batch still loads."""
         torch = self.torch
-        sources = list(sources)
-        names = list(names) if names is not None else [f"<bytes {i}>" for i in range(len(sources))]
+        src_iter = iter(sources)
+        name_iter = iter(names) if names is not None else None
         s_comp, _ = self._stream_ptr()
         s_copy = torch.cuda.Stream(self.device)
         s_d2h = torch.cuda.Stream(self.device)
         ring = [dict() for _ in range(max(1, host_slots))]
+        counter = [0]
 
-        def stage(i):
-            src = sources[i]
+        def stage():
+            try:
+                src = next(src_iter)
+            except StopIteration:
+                return None
+            i = counter[0]
+            counter[0] += 1
+            name = next(name_iter) if name_iter is not None else f"<bytes {i}>"
+            if isinstance(src, Exception):
+                return (name, src)
             if isinstance(src, torch.Tensor) and not src.is_cuda and src.is_pinned():
                 pinned, n = src, int(src.numel())
             else:
@@ -293,15 +303,26 @@ class ViconLoader:
                 d_bytes[:n].copy_(pinned[:n], non_blocking=True)
                 ev = torch.cuda.Event()
                 ev.record(s_copy)
-            return d_bytes, n, ev, pinned
+            return (name, d_bytes, n, ev, pinned)
 
-        nxt = stage(0) if sources else None
-        for i in range(len(sources)):
-            d_bytes, n, ev, pinned = nxt
-            nxt = stage(i + 1) if i + 1 < len(sources) else None
-            s_comp.wait_event(ev)
-            d_bytes.record_stream(s_comp)
-            data = self._run(_Source(d_bytes, n, pinned.numpy()[:n]), names[i])
+        i = 0
+        nxt = stage()
+        while nxt is not None:
+            cur = nxt
+            nxt = stage()  # the next file's host->device copy is in flight while this one is parsed
+            try:
+                if len(cur) == 2:
+                    raise cur[1]
+                name, d_bytes, n, ev, pinned = cur
+                s_comp.wait_event(ev)
+                d_bytes.record_stream(s_comp)
+                data = self._run(_Source(d_bytes, n, pinned.numpy()[:n]), name)
+            except Exception as exc:  # noqa: BLE001
+                if not return_exceptions:
+                    raise
+                yield exc
+                i += 1
+                continue
             if to_host:
                 done = torch.cuda.Event()
                 done.record(s_comp)
@@ -316,7 +337,78 @@ class ViconLoader:
                     blk.tensor.record_stream(s_d2h)
                     blk.prefetch_host(s_d2h, buf)
             yield data
+            i += 1
         s_d2h.synchronize()
+
+    def load_files(self, csv_filenames, to_host: bool = True, host_slots: int = 2, read_ahead: int = 2):
+        """Batch front-end: yields (filename, ViconNexusData) for every
+        file, in order.  A reader thread fills a ring of pinned buffers `read_ahead` files ahead of the
+        GPU; the GPU side is `load_many` (H2D, scan/parse and D2H of consecutive files overlap).
+        A file that fails yields (filename, exception) instead of stopping the batch."""
+        import queue
+        import threading
+
+        torch = self.torch
+        names = [str(f) for f in csv_filenames]
+        # files in use at once: one being parsed, one staged, `read_ahead` queued, one being read
+        ring = [None] * (read_ahead + 3)
+        q = queue.Queue(maxsize=read_ahead)
+
+        def reader():
+            for i, name in enumerate(names):
+                try:
+                    size = os.path.getsize(name)
+                    slot = i % len(ring)
+                    buf = ring[slot]
+                    if buf is None or buf.numel() < _pad16(size):
+                        buf = torch.empty(max(_pad16(size), 1 << 20), dtype=torch.uint8, pin_memory=True)
+                        ring[slot] = buf
+                    with open(name, "rb") as fh:
+                        got = fh.readinto(memoryview(buf.numpy())[:size])
+                    if got != size:
+                        raise IOError(f"short read on {name}: {got} of {size} bytes")
+                    q.put((name, buf[:size]))
+                except Exception as exc:  # noqa: BLE001 - reported with the file it belongs to
+                    q.put((name, exc))
+            q.put(None)
+
+        threading.Thread(target=reader, daemon=True).start()
+
+        def sources():
+            while True:
+                item = q.get()
+                if item is None:
+                    return
+                yield item
+
+        order = []
+
+        def feed():
+            for name, src in sources():
+                order.append(name)
+                yield src
+
+        k = 0
+        for result in self.load_many(feed(), names=_LazyNames(order), to_host=to_host, host_slots=host_slots,
+                                     return_exceptions=True):
+            yield order[k], result
+            k += 1
+
+
+class _LazyNames:
+    """Iterator over a list that is still being appended to (names follow the sources)."""
+
+    def __init__(self, items):
+        self.items = items
+        self.k = 0
+
+    def __iter__(self):
+        return self
+
+    def __next__(self):
+        name = self.items[self.k]
+        self.k += 1
+        return name
 
 
 # ---- planning: which rows are what ------------------------------------------------------------------

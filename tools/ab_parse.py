@@ -36,7 +36,7 @@ for path in sys.argv[2:]:
         s = secs[k]
         s.row_begin, s.row_end, s.num_cols, s.n_keep, s.d_out, s.stride = r0, r1, lay.num_cols, lay.n_keep, blk.data_ptr(), r1 - r0
         k += 1
-    dst = torch.empty(1, dtype=torch.int64, device="cuda")
+    dst = torch.zeros(2, dtype=torch.int64, device="cuda")
     def t(call, reps=20):
         for _ in range(3): call()
         torch.cuda.synchronize()
@@ -48,4 +48,7 @@ for path in sys.argv[2:]:
     ts = t(lambda: L.ms_scan(d.data_ptr(), n, ws.data_ptr(), ws.numel(), dsum.data_ptr(), sptr))
     tp = t(lambda: L.ms_parse(d.data_ptr(), n, ws.data_ptr(), secs, k, dst.data_ptr(), sptr))
     chk = [int(b.view(torch.int64).sum().item()) for b in blocks]
-    print(f"{os.path.basename(path):28s} scan+resolve {ts:.3f} ms  parse {tp:.3f} ms  status {int(dst.item())} checksum {chk}")
+    dst[1] = 0
+    L.ms_parse(d.data_ptr(), n, ws.data_ptr(), secs, k, dst.data_ptr(), sptr)
+    torch.cuda.synchronize()
+    print(f"{os.path.basename(path):28s} scan+resolve {ts:.3f} ms  parse {tp:.3f} ms  status {int(dst[0].item())} aux {int(dst[1].item())} checksum {chk}")
