@@ -214,6 +214,30 @@ def bench_nmf(dev, iters=2000):
     return out
 
 
+def bench_pipeline(loader, d_bytes, n, layout, trials=3):
+    """BASELINE configs[4] per trial: device-resident CSV -> load -> segment -> 8 gait cycles ->
+    envelopes -> NMF sweep k=1..8 x 20 restarts x 200 iterations (1280 problems, one launch);
+    wall clock, results (best restart per cycle and rank, VAF tables) on the host."""
+    import torch
+
+    from muscle_synergies_b200.pipeline import trial_synergies
+
+    def one():
+        data = loader.load_device(d_bytes, n=n, name=layout)
+        return trial_synergies(data, 1, 8, n_restarts=20, random_state=0, max_iter=200, tol=0.0)
+
+    one()
+    torch.cuda.synchronize()
+    t = time.perf_counter()
+    for _ in range(trials):
+        res = one()
+    torch.cuda.synchronize()
+    per_trial = (time.perf_counter() - t) / trials
+    return {"workload": "per trial: load + segment + 8 cycles x (envelope, time-normalise 200) + NMF k=1..8 x 20 restarts x 200 it",
+            "cycles_per_s": len(res.cycles) / per_trial, "ms_per_trial": per_trial * 1e3,
+            "nmf_problems_per_trial": int(len(res.restarts)), "timing": "wall clock incl. host result tables"}
+
+
 # ---- reference arm ----------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -400,6 +424,12 @@ def run_ours(args):
 
     # ---- NMF-MU extension: rank sweep k=1..8 x 20 restarts on 200 x 16 envelopes (configs[3])
     nmf = bench_nmf(dev) if rank == 0 else None
+    pipeline = None
+    if rank == 0:
+        try:
+            pipeline = bench_pipeline(loader, d_bytes, n, layout)
+        except Exception as exc:  # noqa: BLE001
+            pipeline = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
@@ -425,6 +455,7 @@ def run_ours(args):
                          "algorithmic_bytes_per_launch": b_alg, "kernel_ms": t_parse},
             "kernels_ms": {"ms_parse": t_parse, "ms_scan+resolve": t_scan},
             "nmf": nmf,
+            "pipeline": pipeline,
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }

@@ -13,6 +13,7 @@ __version__ = "0.1.0"
 
 from .analysis import SynergyRunResult, find_synergies, nmf_mu_batched, vaf  # noqa: F401
 from .emg import envelope_windows, normalize, rms, time_normalize, zero_center  # noqa: F401
+from .pipeline import synergies_for_files, trial_synergies  # noqa: F401
 from .vicon_data import (  # noqa: F401
     DeviceData,
     DeviceType,
@@ -39,4 +40,6 @@ __all__ = (
     # extensions
     "nmf_mu_batched",
     "envelope_windows",
+    "trial_synergies",
+    "synergies_for_files",
 )

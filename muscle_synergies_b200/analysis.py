@@ -11,6 +11,7 @@ random_state=seed)` at the same iteration count.  Other solvers / inits raise
 NotImplementedError: this stage is an extension, not a replacement of scikit-learn.
 """
 import ctypes
+import functools
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from typing import Mapping, Optional, Sequence, Union
@@ -44,60 +45,109 @@ def sklearn_random_init(X: np.ndarray, k: int, seed: int):
     return W, H
 
 
+def _unit_draws(n: int, m: int, k: int, seed: int):
+    """|standard_normal| draws of sklearn's random init for (seed, k) on an n x m matrix: H first,
+    then W.  The init itself is these times sqrt(X.mean() / k) (|a z| == a |z| exactly for a > 0)."""
+    rng = np.random.RandomState(seed)
+    H = np.abs(rng.standard_normal(size=(k, m)))
+    W = np.abs(rng.standard_normal(size=(n, k)))
+    return W.ravel(), H.ravel()
+
+
+_unit_draws_cached = functools.lru_cache(maxsize=1024)(_unit_draws)  # gait-cycle sized problems only
+_draw_cache = OrderedDict()  # (n, m, ranks, seeds, device) -> unit draws of the whole batch, on the device
+
+
+def _batch_draws(torch, n, m, ranks, seeds, dev):
+    key = (n, m, ranks.tobytes(), seeds.tobytes(), str(dev))
+    hit = _draw_cache.get(key)
+    if hit is None:
+        draws = _unit_draws_cached if n * m <= 1 << 16 else _unit_draws
+        parts = [draws(n, m, int(k), int(s)) for k, s in zip(ranks, seeds)]
+        hit = (torch.from_numpy(np.concatenate([p[0] for p in parts])).to(dev),
+               torch.from_numpy(np.concatenate([p[1] for p in parts])).to(dev))
+        if n * m > 1 << 16:
+            return hit
+        _draw_cache[key] = hit
+        while len(_draw_cache) > 8:
+            _draw_cache.popitem(last=False)
+    else:
+        _draw_cache.move_to_end(key)
+    return hit
+
+
 def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int = 200, tol: float = 1e-4,
                    check_every: int = 10, init=None, device=None, x_index: Optional[Sequence[int]] = None,
                    regime: Optional[str] = None) -> NMFBatchResult:
     """Runs len(ranks) MU factorisations in one kernel launch.
 
     X: non-negative (n samples x m muscles), or a stack (B, n, m) of such matrices (e.g. one per
-    gait cycle) with x_index[p] naming the matrix of problem p.  ranks[p], seeds[p]: rank and
-    sklearn `random_state` of problem p; `init` optionally gives the initial (W, H) pairs
+    gait cycle) with x_index[p] naming the matrix of problem p; a numpy array, or a CUDA tensor
+    (e.g. the output of `envelope_windows`), which then never leaves the device.  ranks[p], seeds[p]:
+    rank and sklearn `random_state` of problem p; `init` optionally gives the initial (W, H) pairs
     instead of the seeds.  regime: None (by size), "resident" or "stream"."""
     import torch
 
     lib = nat.lib()
     if not torch.cuda.is_available():
         raise nat.NativeError("nmf_mu_batched needs a CUDA device; there is no CPU fallback")
-    dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
-    if isinstance(X, torch.Tensor):
-        Xh = X.detach().to("cpu", torch.float64).numpy()
+    on_device = isinstance(X, torch.Tensor) and X.is_cuda
+    if on_device:
+        dev = X.device
+        dX64 = X.detach().to(torch.float64)
+        if dX64.ndim == 2:
+            dX64 = dX64[None]
+        shape = tuple(dX64.shape)
     else:
-        Xh = np.asarray(X, dtype=np.float64)
-    if Xh.ndim == 2:
-        Xh = Xh[None]
-    if Xh.ndim != 3 or Xh.size == 0:
+        dev = torch.device(device if device is not None else f"cuda:{torch.cuda.current_device()}")
+        Xh = X.detach().to("cpu", torch.float64).numpy() if isinstance(X, torch.Tensor) else np.asarray(X, dtype=np.float64)
+        if Xh.ndim == 2:
+            Xh = Xh[None]
+        shape = Xh.shape
+    if len(shape) != 3 or 0 in shape:
         raise ValueError("X must be a non-empty (n, m) matrix or a (B, n, m) stack")
-    if (Xh < 0).any():
+    if bool((dX64 < 0).any()) if on_device else bool((Xh < 0).any()):
         raise ValueError("Negative values in data passed to NMF (input X)")
-    _, n, m = Xh.shape
-    ranks = np.asarray(ranks, dtype=np.int32)
-    seeds = np.asarray(seeds, dtype=np.int64)
+    B, n, m = shape
+    ranks = np.ascontiguousarray(ranks, dtype=np.int32)
+    seeds = np.ascontiguousarray(seeds, dtype=np.int64)
     P = len(ranks)
-    xi = np.zeros(P, dtype=np.int32) if x_index is None else np.asarray(x_index, dtype=np.int32)
-    if len(xi) != P or len(seeds) != P or xi.min() < 0 or xi.max() >= Xh.shape[0]:
+    xi = np.zeros(P, dtype=np.int32) if x_index is None else np.ascontiguousarray(x_index, dtype=np.int32)
+    if P < 1 or len(xi) != P or len(seeds) != P or xi.min() < 0 or xi.max() >= B:
         raise ValueError("ranks, seeds and x_index must have one entry per problem")
+    if ranks.min() < 1:
+        raise ValueError("ranks must be positive")
     kmax = int(ranks.max())
     # short signals stay resident in shared memory; long ones stream from HBM every iteration
     resident = (n <= int(lib.ms_nmf_resident_max_rows(m, kmax))) if regime is None else (regime == "resident")
-    w_parts, h_parts = [], []
-    for p in range(P):
-        if init is not None:
-            W0, H0 = init[p]
-        else:
-            W0, H0 = sklearn_random_init(Xh[xi[p]], int(ranks[p]), int(seeds[p]))  # float64 draws, like sklearn
-        w_parts.append(np.ascontiguousarray(W0, dtype=np.float32).ravel())
-        h_parts.append(np.ascontiguousarray(H0, dtype=np.float32).ravel())
     stream = torch.cuda.current_stream(dev)
     with torch.cuda.device(dev):
-        dX = torch.from_numpy(np.ascontiguousarray(Xh, dtype=np.float32)).to(dev)
-        dW = torch.from_numpy(np.concatenate(w_parts)).to(dev)
-        dH = torch.from_numpy(np.concatenate(h_parts)).to(dev)
+        if on_device:
+            dX = dX64.to(torch.float32).contiguous()
+        else:
+            dX = torch.from_numpy(np.ascontiguousarray(Xh, dtype=np.float32)).to(dev)
+        if init is not None:
+            dW = torch.from_numpy(np.concatenate(
+                [np.ascontiguousarray(init[p][0], dtype=np.float32).ravel() for p in range(P)])).to(dev)
+            dH = torch.from_numpy(np.concatenate(
+                [np.ascontiguousarray(init[p][1], dtype=np.float32).ravel() for p in range(P)])).to(dev)
+        else:
+            # sklearn's init="random": float64 draws scaled by sqrt(X.mean() / k), then the kernel's fp32
+            unit_w, unit_h = _batch_draws(torch, n, m, ranks, seeds, dev)
+            if on_device:
+                means = dX64.mean(dim=(1, 2))
+            else:
+                means = torch.from_numpy(np.array([Xh[b].mean() for b in range(B)])).to(dev)
+            d_ranks = torch.from_numpy(ranks.astype(np.int64)).to(dev)
+            avg = torch.sqrt(means[torch.from_numpy(xi.astype(np.int64)).to(dev)] / d_ranks)
+            dW = (unit_w * torch.repeat_interleave(avg, d_ranks * n)).to(torch.float32)
+            dH = (unit_h * torch.repeat_interleave(avg, d_ranks * m)).to(torch.float32)
         work = torch.empty(max(P * 32, int(lib.ms_nmf_stream_workspace_bytes(m, P))), dtype=torch.uint8, device=dev)
         d_iter = torch.empty(P, dtype=torch.int32, device=dev)
         d_err = torch.empty(P, dtype=torch.float32, device=dev)
         d_vaf = torch.empty((P, m + 1), dtype=torch.float32, device=dev)
-        h_ranks = (ctypes.c_int32 * P)(*[int(k) for k in ranks])
-        h_xi = (ctypes.c_int32 * P)(*[int(v) for v in xi])
+        h_ranks = ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+        h_xi = xi.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
         entry = lib.ms_nmf_mu_batched if resident else lib.ms_nmf_mu_stream
         nat.check(
             entry(
@@ -109,14 +159,10 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         )
         Wall, Hall = dW.cpu().numpy(), dH.cpu().numpy()
         n_iter, err, vafs = d_iter.cpu().numpy(), d_err.cpu().numpy(), d_vaf.cpu().numpy()
-    Ws, Hs = [], []
-    wo = ho = 0
-    for k in ranks:
-        k = int(k)
-        Ws.append(Wall[wo : wo + n * k].reshape(n, k))
-        Hs.append(Hall[ho : ho + k * m].reshape(k, m))
-        wo += n * k
-        ho += k * m
+    w_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * n)])
+    h_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * m)])
+    Ws = [Wall[w_off[p] : w_off[p + 1]].reshape(n, int(ranks[p])) for p in range(P)]
+    Hs = [Hall[h_off[p] : h_off[p + 1]].reshape(int(ranks[p]), m) for p in range(P)]
     return NMFBatchResult(ranks, seeds, Ws, Hs, n_iter, err, vafs)
 
 

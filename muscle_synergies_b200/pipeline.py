@@ -1,0 +1,125 @@
+"""Trial -> gait cycles -> envelopes -> synergies, without leaving the GPU (BASELINE configs[4]).
+
+The flow of the reference's tutorial "Finding muscle synergies" (docs/source/tutorials, cells
+4-30) applied per gait cycle, as SURVEY.md section 8d configs[4] spells it out:
+
+    data = load_vicon_file(f)                       load_csv.py:96-135          (ms_scan + ms_parse)
+    seg = Segmenter(data)                           project/segment.py:124-298  (ms_find_transitions)
+    for each trecho, cycle:
+        emg = data.emg[seg.get_times_of(trecho, cycle)]                          (window bounds only)
+        env = normalize(time_normalize(rms(zero_center(emg), 0.5 s), 200))       analysis.py:230-594
+        find_synergies(env, 1, 8, solver="mu", init="random", random_state=s)    analysis.py:713-914
+
+Here the envelope is computed once per trial (zero-centred moving RMS over the whole recording,
+then every cycle is resampled and amplitude-normalised - `emg.envelope_windows`) and all
+cycles x ranks x restarts run as ONE launch of the batched NMF kernel on the device-resident
+envelopes.  This module is an extension: the reference has no batch entry point.
+"""
+from dataclasses import dataclass, field
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+
+import numpy as np
+import pandas
+
+from .analysis import NMFBatchResult, nmf_mu_batched
+from .emg import envelope_windows
+from .segment import Cycle, Segmenter, Trecho
+from .vicon_data import ViconLoader, ViconNexusData
+
+
+@dataclass
+class CycleSynergies:
+    """Synergies of one gait cycle: per rank, the restart with the smallest reconstruction error."""
+
+    trecho: Trecho
+    cycle: Cycle
+    window: slice  # (frame, subframe) slice, as Segmenter.get_times_of returns it
+    vaf_values: pandas.DataFrame  # index: rank; columns: "All signals" + muscles  (analysis.py:884-894)
+    components: Dict[int, pandas.DataFrame]  # rank -> (rank x muscles) synergy vectors
+    transformed: Dict[int, np.ndarray]  # rank -> (reduce_to x rank) activations
+    n_iter: Dict[int, int]
+    reconstruction_err: Dict[int, float]
+    random_state: Dict[int, int]
+
+
+@dataclass
+class TrialSynergies:
+    cycles: List[CycleSynergies]
+    restarts: pandas.DataFrame  # one row per (trecho, cycle, rank, restart): seed, n_iter, err, overall VAF
+    envelopes: object = field(repr=False, default=None)  # (n_cycles, reduce_to, muscles) float64 CUDA tensor
+    batch: Optional[NMFBatchResult] = field(repr=False, default=None)
+
+    def __getitem__(self, key: Tuple[Trecho, Cycle]) -> CycleSynergies:
+        trecho, cycle = Segmenter._parse_trecho(key[0]), Segmenter._parse_cycle(key[1])
+        for c in self.cycles:
+            if c.trecho is trecho and c.cycle is cycle:
+                return c
+        raise KeyError(key)
+
+
+def cycle_windows(segmenter: Segmenter) -> List[Tuple[Trecho, Cycle, slice]]:
+    """The 4 trechos x 2 cycles of a trial, each first.start .. fourth.stop (segment.py:221-232)."""
+    return [(t, c, segmenter.get_times_of(t, c)) for t in Trecho for c in Cycle]
+
+
+def trial_synergies(data: ViconNexusData, min_components: int = 1, max_components: int = 8, n_restarts: int = 20,
+                    random_state: int = 0, max_iter: int = 200, tol: float = 1e-4, window_size: float = 0.5,
+                    reduce_to: int = 200, segmenter: Optional[Segmenter] = None, keep_batch: bool = False) -> TrialSynergies:
+    """Segments a loaded trial and factorises the EMG envelope of each of its 8 gait cycles for
+    every rank in [min_components, max_components] from `n_restarts` random initialisations
+    (seeds random_state .. random_state + n_restarts - 1, sklearn `init="random"` draws)."""
+    muscles = data.emg.columns
+    if not 1 <= min_components <= max_components <= len(muscles):
+        raise ValueError("invalid number of components")
+    if n_restarts < 1:
+        raise ValueError("n_restarts must be positive")
+    seg = segmenter if segmenter is not None else Segmenter(data)
+    wins = cycle_windows(seg)
+    env = envelope_windows(data.emg, [w for (_, _, w) in wins], window_size=window_size, reduce_to=reduce_to)
+    sweep = list(range(min_components, max_components + 1))
+    n_cyc, n_k = len(wins), len(sweep)
+    # problem order: cycle-major, then rank, then restart
+    ranks = np.tile(np.repeat(np.array(sweep, dtype=np.int32), n_restarts), n_cyc)
+    seeds = np.tile(np.arange(random_state, random_state + n_restarts, dtype=np.int64), n_cyc * n_k)
+    x_index = np.repeat(np.arange(n_cyc, dtype=np.int32), n_k * n_restarts)
+    res = nmf_mu_batched(env, ranks, seeds, max_iter=max_iter, tol=tol, x_index=x_index)
+
+    labels = ["All signals"] + muscles
+    err = res.err.reshape(n_cyc, n_k, n_restarts)
+    best = err.argmin(axis=2)
+    cycles = []
+    for ci, (trecho, cycle, window) in enumerate(wins):
+        rows, comps, acts, iters, errs, rstate = [], {}, {}, {}, {}, {}
+        for ki, k in enumerate(sweep):
+            p = (ci * n_k + ki) * n_restarts + int(best[ci, ki])
+            rows.append(res.vaf[p].astype(np.float64))
+            comps[k] = pandas.DataFrame(res.H[p].astype(np.float64), columns=muscles)
+            acts[k] = res.W[p].astype(np.float64)
+            iters[k], errs[k], rstate[k] = int(res.n_iter[p]), float(res.err[p]), int(res.seeds[p])
+        vaf_values = pandas.DataFrame(np.array(rows), columns=labels, index=np.array(sweep))
+        cycles.append(CycleSynergies(trecho, cycle, window, vaf_values, comps, acts, iters, errs, rstate))
+    restarts = pandas.DataFrame({
+        "trecho": np.repeat([t.value for (t, _, _) in wins], n_k * n_restarts),
+        "cycle": np.repeat([c.value for (_, c, _) in wins], n_k * n_restarts),
+        "n_components": ranks,
+        "random_state": seeds,
+        "n_iter": res.n_iter,
+        "reconstruction_err": res.err.astype(np.float64),
+        "All signals": res.vaf[:, 0].astype(np.float64),
+    })
+    return TrialSynergies(cycles, restarts, env, res if keep_batch else None)
+
+
+def synergies_for_files(paths: Sequence[str], loader: Optional[ViconLoader] = None, **kwargs) -> Iterable[Tuple[str, TrialSynergies]]:
+    """`trial_synergies` over a list of trial files; the next file is read and uploaded while the
+    current one is analysed (ViconLoader.load_files).  Yields (path, TrialSynergies) in order; a
+    file that fails to load or to segment yields (path, exception) instead."""
+    loader = loader if loader is not None else ViconLoader()
+    for path, data in loader.load_files(paths, to_host=False):
+        if isinstance(data, Exception):
+            yield path, data
+            continue
+        try:
+            yield path, trial_synergies(data, **kwargs)
+        except (ValueError, IndexError, KeyError) as exc:  # e.g. fewer than 40 transitions in the trial
+            yield path, exc

@@ -310,6 +310,11 @@ class DeviceData:
         return self._block.tensor[c0 : c0 + len(self._coords), : self._block.n_rows]
 
     @property
+    def columns(self):
+        """Column names of `df`, without materialising it on the host."""
+        return list(self._coords)
+
+    @property
     def values_cm(self) -> np.ndarray:
         """(n_columns, n_rows) host array, channel-major (the block layout of `df`)."""
         c0 = self._first_channel
