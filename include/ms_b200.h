@@ -135,6 +135,18 @@ int ms_channel_means(const double* d_src, int64_t stride, int32_t n_channels, in
  * channel; d_mean may be NULL (no centring).  window <= n. */
 int ms_rms_envelope(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const double* d_mean,
                     int32_t window, double* d_out, int64_t out_stride, void* stream);
+/* digital_filter (analysis.py:314-432): scipy.signal.sosfilt (zero_lag == 0: forward, from rest) or
+ * sosfiltfilt (zero_lag != 0: odd extension by padlen samples, forward and backward runs started at
+ * h_zi * first sample) along time, per channel.  h_sos: [n_sections][6] = b0 b1 b2 1 a1 a2 (scipy's
+ * layout, host memory, n_sections <= 8); h_zi: [n_sections][2] = scipy.signal.sosfilt_zi(sos) (host;
+ * only read when zero_lag); padlen: sosfiltfilt's (n > padlen), 0 when zero_lag == 0.
+ * linear_envelope (analysis.py:252-311) is the same call with the rectification fused into the loads:
+ * the filter input is x - d_mean[channel] (d_mean NULL: x), and its absolute value when rectify != 0.
+ * d_work: ms_sosfilt_workspace_bytes(n, n_channels, padlen, zero_lag) bytes of device memory. */
+size_t ms_sosfilt_workspace_bytes(int64_t n, int32_t n_channels, int64_t padlen, int32_t zero_lag);
+int ms_sosfilt(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const double* h_sos,
+               int32_t n_sections, const double* h_zi, int64_t padlen, int32_t zero_lag, const double* d_mean,
+               int32_t rectify, double* d_out, int64_t out_stride, void* d_work, void* stream);
 /* time_normalize (analysis.py:551-594, linear) of rows [start_w, stop_w) onto reduce_to points,
  * then (normalize != 0) normalize (analysis.py:510-525): divide by the column max |.|.
  * d_out: [n_windows][reduce_to][n_channels] (samples x muscles, the orientation NMF takes). */

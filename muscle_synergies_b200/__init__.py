@@ -12,7 +12,15 @@ there is no CPU fallback.
 __version__ = "0.1.0"
 
 from .analysis import SynergyRunResult, find_synergies, nmf_mu_batched, vaf  # noqa: F401
-from .emg import envelope_windows, normalize, rms, time_normalize, zero_center  # noqa: F401
+from .emg import (  # noqa: F401
+    digital_filter,
+    envelope_windows,
+    linear_envelope,
+    normalize,
+    rms,
+    time_normalize,
+    zero_center,
+)
 from .pipeline import synergies_for_files, trial_synergies  # noqa: F401
 from .vicon_data import (  # noqa: F401
     DeviceData,
@@ -32,6 +40,8 @@ __all__ = (
     "DeviceType",
     # analysis.py names of the reference that have a CUDA implementation here
     "zero_center",
+    "linear_envelope",
+    "digital_filter",
     "rms",
     "normalize",
     "time_normalize",

@@ -69,6 +69,9 @@ def _declare(L):
         "ms_cut_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp]),
         "ms_channel_means": (ctypes.c_int, [vp, i64, i32, i64, vp, vp]),
         "ms_rms_envelope": (ctypes.c_int, [vp, i64, i32, i64, vp, i32, vp, i64, vp]),
+        "ms_sosfilt_workspace_bytes": (ctypes.c_size_t, [i64, i32, i64, i32]),
+        "ms_sosfilt": (ctypes.c_int, [vp, i64, i32, i64, ctypes.POINTER(ctypes.c_double), i32,
+                                      ctypes.POINTER(ctypes.c_double), i64, i32, vp, i32, vp, i64, vp, vp]),
         "ms_time_normalize_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, i32, i32, i32, vp, vp]),
         "ms_nmf_resident_max_rows": (i32, [i32, i32]),
         "ms_nmf_mu_batched": (ctypes.c_int, [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, vp, i32,

@@ -9,6 +9,7 @@
 // float64 throughout; sums are ordered differently from numpy's, so parity with the reference
 // functions is to a stated tolerance (tests/test_emg_gpu.py), not bit-exact.
 #include <stdio.h>
+#include <string.h>
 
 #include "ms_common.cuh"
 
@@ -97,6 +98,234 @@ extern "C" int ms_rms_envelope(const double* d_src, int64_t stride, int32_t n_ch
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
+}
+
+// ---- IIR filtering: cascaded second-order sections, forward or zero-lag -------------------------------
+// digital_filter (analysis.py:314-432) applies scipy.signal.sosfilt / sosfiltfilt along time; linear_envelope
+// (analysis.py:252-311) is zero-centre -> abs -> that low-pass.  A recursion along time is a serial
+// chain per channel, so the signal is cut into chunks of SOS_CHUNK samples that run in parallel:
+//   transition  M = state after SOS_CHUNK steps of zero input from each unit state (the filter is linear)
+//   zero-state  every chunk from a zero state                     -> its final state f_c
+//   carry       per channel, over the chunks: z_{c+1} = M z_c + f_c   (the only serial part)
+//   final       every chunk again from its true start state z_c   -> the outputs
+// Each section is scipy's direct-form-II-transposed step (scipy/signal/_sosfilt.pyx:_sosfilt_float).
+// sosfiltfilt = odd extension by padlen samples on both ends, forward run started at zi * ext[0], backward run
+// over the reversed result started at zi * (its first sample), reversed again, extension dropped
+// (scipy/signal/_signaltools.py:sosfiltfilt); the extension and the rectification are generated on the fly.
+#define SOS_CHUNK 1024
+#define SOS_MAX_SECTIONS 8
+
+struct MsSosCoef {
+    double b0[SOS_MAX_SECTIONS], b1[SOS_MAX_SECTIONS], b2[SOS_MAX_SECTIONS], a1[SOS_MAX_SECTIONS], a2[SOS_MAX_SECTIONS];
+    double zi[2 * SOS_MAX_SECTIONS];  // steady-state initial condition per unit input (sosfilt_zi), zero for a plain sosfilt
+};
+struct MsSosIo {
+    const double* src;  // forward: the recording [channel][stride]; backward: the forward result [channel][N]
+    int64_t src_stride;
+    int64_t n;       // samples of the recording
+    int64_t padlen;  // odd extension on both sides (0: none)
+    const double* mean;  // forward only: subtracted first (NULL: nothing)
+    int rectify;         // forward only: |x - mean|
+    int backward;        // 0: forward over the extended recording, 1: backward over src
+    double* dst;         // [channel][dst_stride]; forward: all N samples, backward: the extension dropped
+    int64_t dst_stride;
+};
+
+__device__ __forceinline__ double ms_sos_value(const MsSosIo& io, const double* __restrict__ x, double mu, int64_t k) {
+    const double v = x[k] - mu;
+    return io.rectify ? fabs(v) : v;
+}
+// sample i of the sequence this pass filters (N = n + 2 padlen of them)
+__device__ __forceinline__ double ms_sos_input(const MsSosIo& io, const double* __restrict__ x, double mu, int64_t i,
+                                               int64_t N) {
+    if (io.backward) return x[N - 1 - i];
+    const int64_t j = i - io.padlen;
+    if (j < 0) return 2.0 * ms_sos_value(io, x, mu, 0) - ms_sos_value(io, x, mu, io.padlen - i);
+    if (j >= io.n) return 2.0 * ms_sos_value(io, x, mu, io.n - 1) - ms_sos_value(io, x, mu, io.n - 2 - (j - io.n));
+    return ms_sos_value(io, x, mu, j);
+}
+
+template <int S>
+__device__ __forceinline__ double ms_sos_step(const MsSosCoef& c, double (&z)[2 * S], double x) {
+#pragma unroll
+    for (int s = 0; s < S; s++) {
+        const double y = c.b0[s] * x + z[2 * s];
+        z[2 * s] = c.b1[s] * x - c.a1[s] * y + z[2 * s + 1];
+        z[2 * s + 1] = c.b2[s] * x - c.a2[s] * y;
+        x = y;
+    }
+    return x;
+}
+
+template <int S>
+__global__ void ms_sos_transition_kernel(MsSosCoef c, double* __restrict__ M) {
+    const int j = threadIdx.x;  // unit state j
+    if (j >= 2 * S) return;
+    double z[2 * S];
+#pragma unroll
+    for (int i = 0; i < 2 * S; i++) z[i] = i == j ? 1.0 : 0.0;
+    for (int t = 0; t < SOS_CHUNK; t++) ms_sos_step<S>(c, z, 0.0);
+#pragma unroll
+    for (int i = 0; i < 2 * S; i++) M[i * 2 * S + j] = z[i];
+}
+
+// FINAL = 0: zero-state run, writes the chunk's final state; FINAL = 1: run from the carried state, writes the outputs
+template <int S, int FINAL>
+__global__ void __launch_bounds__(64)
+    ms_sos_chunk_kernel(MsSosCoef c, MsSosIo io, int64_t N, int64_t n_chunks, double* __restrict__ state) {
+    const int64_t chunk = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const int ch = blockIdx.y;
+    if (chunk >= n_chunks) return;
+    const double* __restrict__ x = io.src + (int64_t)ch * io.src_stride;
+    const double mu = (!io.backward && io.mean) ? io.mean[ch] : 0.0;
+    double* __restrict__ st = state + ((int64_t)ch * n_chunks + chunk) * (2 * S);
+    double z[2 * S];
+#pragma unroll
+    for (int i = 0; i < 2 * S; i++) z[i] = FINAL ? st[i] : 0.0;
+    const int64_t i0 = chunk * SOS_CHUNK, i1 = min(N, i0 + SOS_CHUNK);
+    if (!FINAL) {
+        for (int64_t i = i0; i < i1; i++) ms_sos_step<S>(c, z, ms_sos_input(io, x, mu, i, N));
+#pragma unroll
+        for (int k = 0; k < 2 * S; k++) st[k] = z[k];
+    } else if (!io.backward) {
+        double* __restrict__ y = io.dst + (int64_t)ch * io.dst_stride;
+        for (int64_t i = i0; i < i1; i++) y[i] = ms_sos_step<S>(c, z, ms_sos_input(io, x, mu, i, N));
+    } else {
+        double* __restrict__ y = io.dst + (int64_t)ch * io.dst_stride;
+        for (int64_t i = i0; i < i1; i++) {
+            const double v = ms_sos_step<S>(c, z, ms_sos_input(io, x, mu, i, N));
+            const int64_t j = N - 1 - i - io.padlen;  // position in the recording
+            if (j >= 0 && j < io.n) y[j] = v;
+        }
+    }
+}
+
+// one thread per channel: turns the zero-state final states into every chunk's start state, in place
+template <int S>
+__global__ void ms_sos_carry_kernel(MsSosCoef c, MsSosIo io, int64_t N, int64_t n_chunks, int n_channels,
+                                    const double* __restrict__ M, double* __restrict__ state) {
+    const int ch = blockIdx.x * blockDim.x + threadIdx.x;
+    if (ch >= n_channels) return;
+    const double* __restrict__ x = io.src + (int64_t)ch * io.src_stride;
+    const double mu = (!io.backward && io.mean) ? io.mean[ch] : 0.0;
+    const double first = ms_sos_input(io, x, mu, 0, N);
+    double m[2 * S][2 * S], z[2 * S];
+#pragma unroll
+    for (int i = 0; i < 2 * S; i++) {
+        z[i] = c.zi[i] * first;
+#pragma unroll
+        for (int j = 0; j < 2 * S; j++) m[i][j] = M[i * 2 * S + j];
+    }
+    double* __restrict__ st = state + (int64_t)ch * n_chunks * (2 * S);
+    double f[2 * S];
+#pragma unroll
+    for (int i = 0; i < 2 * S; i++) f[i] = st[i];
+    for (int64_t k = 0; k < n_chunks; k++) {
+        double fn[2 * S];
+        const int64_t kn = k + 1 < n_chunks ? k + 1 : k;  // next chunk's loads overlap this chunk's arithmetic
+#pragma unroll
+        for (int i = 0; i < 2 * S; i++) fn[i] = st[kn * (2 * S) + i];
+        double zn[2 * S];
+#pragma unroll
+        for (int i = 0; i < 2 * S; i++) {
+            st[k * (2 * S) + i] = z[i];
+            double acc = f[i];
+#pragma unroll
+            for (int j = 0; j < 2 * S; j++) acc += m[i][j] * z[j];
+            zn[i] = acc;
+        }
+#pragma unroll
+        for (int i = 0; i < 2 * S; i++) {
+            z[i] = zn[i];
+            f[i] = fn[i];
+        }
+    }
+}
+
+template <int S>
+static int ms_sos_run(const MsSosCoef& c, MsSosIo io, int n_channels, double* M, double* state, cudaStream_t st) {
+    const int64_t N = io.n + 2 * io.padlen;
+    const int64_t n_chunks = (N + SOS_CHUNK - 1) / SOS_CHUNK;
+    const dim3 grid((unsigned)((n_chunks + 63) / 64), n_channels);
+    ms_sos_chunk_kernel<S, 0><<<grid, 64, 0, st>>>(c, io, N, n_chunks, state);
+    MS_COUNT_LAUNCH();
+    ms_sos_carry_kernel<S><<<(n_channels + 31) / 32, 32, 0, st>>>(c, io, N, n_chunks, n_channels, M, state);
+    MS_COUNT_LAUNCH();
+    ms_sos_chunk_kernel<S, 1><<<grid, 64, 0, st>>>(c, io, N, n_chunks, state);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}
+
+template <int S>
+static int ms_sosfilt_impl(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const MsSosCoef& c,
+                           int64_t padlen, int zero_lag, const double* d_mean, int rectify, double* d_out,
+                           int64_t out_stride, double* work, cudaStream_t st) {
+    const int64_t N = n + 2 * padlen;
+    const int64_t n_chunks = (N + SOS_CHUNK - 1) / SOS_CHUNK;
+    double* M = work;
+    double* state = M + 4 * SOS_MAX_SECTIONS * SOS_MAX_SECTIONS;
+    double* tmp = state + (int64_t)n_channels * n_chunks * 2 * SOS_MAX_SECTIONS;
+    ms_sos_transition_kernel<S><<<1, 32, 0, st>>>(c, M);
+    MS_COUNT_LAUNCH();
+    MsSosIo io;
+    io.src = d_src, io.src_stride = stride, io.n = n, io.padlen = padlen, io.mean = d_mean, io.rectify = rectify;
+    io.backward = 0;
+    if (!zero_lag) {  // sosfilt: forward, from rest, straight into the output
+        io.dst = d_out, io.dst_stride = out_stride;
+        return ms_sos_run<S>(c, io, n_channels, M, state, st);
+    }
+    io.dst = tmp, io.dst_stride = N;
+    int rc = ms_sos_run<S>(c, io, n_channels, M, state, st);
+    if (rc != MS_OK) return rc;
+    io.src = tmp, io.src_stride = N, io.mean = nullptr, io.rectify = 0, io.backward = 1;
+    io.dst = d_out, io.dst_stride = out_stride;
+    return ms_sos_run<S>(c, io, n_channels, M, state, st);
+}
+
+extern "C" size_t ms_sosfilt_workspace_bytes(int64_t n, int32_t n_channels, int64_t padlen, int32_t zero_lag) {
+    if (n < 0 || n_channels < 0 || padlen < 0) return 0;
+    const int64_t N = n + 2 * padlen;
+    const int64_t n_chunks = (N + SOS_CHUNK - 1) / SOS_CHUNK;
+    size_t doubles = 4 * SOS_MAX_SECTIONS * SOS_MAX_SECTIONS + (size_t)n_channels * n_chunks * 2 * SOS_MAX_SECTIONS;
+    if (zero_lag) doubles += (size_t)n_channels * N;
+    return doubles * sizeof(double);
+}
+
+extern "C" int ms_sosfilt(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const double* h_sos,
+                          int32_t n_sections, const double* h_zi, int64_t padlen, int32_t zero_lag, const double* d_mean,
+                          int32_t rectify, double* d_out, int64_t out_stride, void* d_work, void* stream) {
+    if (!d_src || !d_out || !h_sos || !d_work || n_channels < 1 || n < 1 || n_sections < 1 ||
+        n_sections > SOS_MAX_SECTIONS || padlen < 0)
+        return MS_E_INVALID;
+    if (zero_lag && (!h_zi || n <= padlen)) return MS_E_INVALID;
+    if (!zero_lag && padlen != 0) return MS_E_INVALID;
+    MsSosCoef c;
+    memset(&c, 0, sizeof(c));
+    for (int s = 0; s < n_sections; s++) {
+        const double* r = h_sos + 6 * s;  // b0 b1 b2 a0 a1 a2, a0 == 1 (scipy's sos layout)
+        if (r[3] != 1.0) return MS_E_INVALID;
+        c.b0[s] = r[0], c.b1[s] = r[1], c.b2[s] = r[2], c.a1[s] = r[4], c.a2[s] = r[5];
+        if (zero_lag) c.zi[2 * s] = h_zi[2 * s], c.zi[2 * s + 1] = h_zi[2 * s + 1];
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    double* work = (double*)d_work;
+#define MS_SOS_CASE(S)                                                                                                  \
+    case S:                                                                                                             \
+        return ms_sosfilt_impl<S>(d_src, stride, n_channels, n, c, padlen, zero_lag, d_mean, rectify, d_out, out_stride, \
+                                  work, st);
+    switch (n_sections) {
+        MS_SOS_CASE(1)
+        MS_SOS_CASE(2)
+        MS_SOS_CASE(3)
+        MS_SOS_CASE(4)
+        MS_SOS_CASE(5)
+        MS_SOS_CASE(6)
+        MS_SOS_CASE(7)
+        MS_SOS_CASE(8)
+    }
+#undef MS_SOS_CASE
+    return MS_E_INVALID;
 }
 
 // ---- time normalisation + amplitude normalisation per window -------------------------------------------

@@ -1,8 +1,9 @@
 """EMG envelope chain on the GPU (SURVEY.md section 8f, rank 1 "next" row).
 
 Mirrors of the reference's preprocessing functions (src/muscle_synergies/analysis.py):
-`zero_center` (:230-249), `rms` (:435-507), `normalize` (:510-525), `time_normalize`
-(:551-594, kind="linear"), same signatures on DataFrames, plus `envelope_windows`, which keeps
+`zero_center` (:230-249), `linear_envelope` (:252-311), `digital_filter` (:314-432), `rms`
+(:435-507), `normalize` (:510-525), `time_normalize` (:551-594, kind="linear"), same signatures
+on DataFrames, plus `envelope_windows`, which keeps
 everything in HBM between the cut windows and the NMF stage: trial-wide zero-centred moving RMS,
 then per window linear time-normalisation to `reduce_to` samples and division by the column
 maximum - the flow of docs/source/tutorials "Finding muscle synergies" (cells 10-23) applied
@@ -62,6 +63,61 @@ def rms_envelope(x, window: int, mean=None):
     return out
 
 
+def filter_coeffs(critical_freqs, sampling_frequency: int, order: int, filter_type: str = "butter",
+                  band_type: str = "lowpass", cheby_param: Optional[float] = None) -> np.ndarray:
+    """Second-order sections of the filter, designed on the host by the scipy calls the reference
+    makes (analysis.py:386-409): a handful of numbers; the recursion over the samples is the GPU's."""
+    from scipy import signal
+
+    if filter_type not in {"butter", "cheby1", "cheby2"}:
+        raise ValueError("filter type not understood.")
+    if filter_type == "butter":
+        return signal.butter(order, critical_freqs, btype=band_type, output="sos", fs=sampling_frequency)
+    design = signal.cheby1 if filter_type == "cheby1" else signal.cheby2
+    return design(order, cheby_param, critical_freqs, btype=band_type, output="sos", fs=sampling_frequency)
+
+
+def sos_filter(x, sos: np.ndarray, zero_lag: bool = True, mean=None, rectify: bool = False):
+    """scipy.signal.sosfiltfilt (zero_lag) or sosfilt along every row of a (channels, samples) float64
+    CUDA tensor; with `mean` / `rectify` the input is |x - mean| (the linear envelope's rectifier, fused)."""
+    torch = _torch()
+    from scipy import signal
+
+    x = x if x.stride(1) == 1 else x.contiguous()
+    n_ch, n = int(x.shape[0]), int(x.shape[1])
+    sos = np.ascontiguousarray(sos, dtype=np.float64)
+    if sos.ndim != 2 or sos.shape[1] != 6:
+        raise ValueError("sos array must be 2D with shape (n_sections, 6)")
+    n_sections = sos.shape[0]
+    if n_sections > 8:
+        raise NotImplementedError("the CUDA filter holds up to 8 second-order sections (order 16)")
+    if not np.all(sos[:, 3] == 1.0):
+        raise ValueError("sos[:, 3] should be all ones")
+    padlen, zi = 0, None
+    if zero_lag:
+        # sosfiltfilt's default padding (scipy/signal/_signaltools.py): 3 * ntaps, odd extension
+        ntaps = 2 * n_sections + 1
+        ntaps -= min(int((sos[:, 2] == 0).sum()), int((sos[:, 5] == 0).sum()))
+        padlen = 3 * ntaps
+        if n <= padlen:
+            raise ValueError("The length of the input vector x must be greater than padlen, which is %d." % padlen)
+        zi = np.ascontiguousarray(signal.sosfilt_zi(sos), dtype=np.float64)
+    lib = nat.lib()
+    out = torch.empty((n_ch, n), dtype=torch.float64, device=x.device)
+    if n_ch == 0 or n == 0:
+        return out
+    work = torch.empty(int(lib.ms_sosfilt_workspace_bytes(n, n_ch, padlen, int(zero_lag))), dtype=torch.uint8, device=x.device)
+    dptr = ctypes.POINTER(ctypes.c_double)
+    nat.check(
+        lib.ms_sosfilt(x.data_ptr(), int(x.stride(0)), n_ch, n, sos.ctypes.data_as(dptr), n_sections,
+                       zi.ctypes.data_as(dptr) if zi is not None else None, padlen, int(zero_lag),
+                       mean.data_ptr() if mean is not None else None, int(bool(rectify)), out.data_ptr(), n,
+                       work.data_ptr(), _stream(torch, x.device)),
+        "ms_sosfilt",
+    )
+    return out
+
+
 def time_normalize_windows(env, starts: Sequence[int], stops: Sequence[int], reduce_to: int, normalize: bool = True):
     """(n_windows, reduce_to, channels) float64 CUDA tensor from a (channels, samples) envelope."""
     torch = _torch()
@@ -78,16 +134,27 @@ def time_normalize_windows(env, starts: Sequence[int], stops: Sequence[int], red
     return out
 
 
-def envelope_windows(device, windows, window_size: float = 0.5, reduce_to: int = 200, normalize: bool = True):
-    """Trial-wide zero-centred RMS envelope of a DeviceData (EMG), then every (frame, subframe)
-    window resampled to `reduce_to` points and amplitude-normalised.  Stays on the GPU.
+def envelope_windows(device, windows, window_size: float = 0.5, reduce_to: int = 200, normalize: bool = True,
+                     method: str = "rms", critical_freqs=None, order: int = 4, filter_type: str = "butter",
+                     cheby_param: Optional[float] = None):
+    """Trial-wide envelope of a DeviceData (EMG), then every (frame, subframe) window resampled to
+    `reduce_to` points and amplitude-normalised.  Stays on the GPU.
 
+    method="rms": zero-centred moving RMS over `window_size` seconds (the tutorial's choice);
+    method="linear_envelope": zero-centre, rectify, zero-lag low-pass at `critical_freqs` Hz.
     Returns (n_windows, reduce_to, n_muscles) float64 - each [w] is the X of one NMF problem."""
     x = device.tensor
     n = int(x.shape[1])
-    win = round(window_size * device.sampling_frequency)
     mean = channel_means(x)
-    env = rms_envelope(x, win, mean)
+    if method == "rms":
+        env = rms_envelope(x, round(window_size * device.sampling_frequency), mean)
+    elif method == "linear_envelope":
+        if critical_freqs is None:
+            raise ValueError("linear_envelope needs critical_freqs (the low-pass cut-off in Hz)")
+        sos = filter_coeffs(critical_freqs, device.sampling_frequency, order, filter_type, "lowpass", cheby_param)
+        env = sos_filter(x, sos, zero_lag=True, mean=mean, rectify=True)
+    else:
+        raise ValueError('method must be "rms" or "linear_envelope"')
     idx = [device.to_index(w) for w in windows]
     starts = [s.indices(n)[0] for s in idx]
     stops = [max(s.indices(n)[0], s.indices(n)[1]) for s in idx]
@@ -106,6 +173,23 @@ def zero_center(signal_df: pandas.DataFrame, inplace: bool = False) -> pandas.Da
     x = _channel_major(signal_df)
     centred = x - channel_means(x)[:, None]
     return _like(signal_df, inplace, centred.T.cpu().numpy())
+
+
+def digital_filter(signal_df: pandas.DataFrame, critical_freqs, sampling_frequency: int, order: int,
+                   filter_type: str = "butter", band_type: str = "lowpass", zero_lag: bool = True,
+                   cheby_param: Optional[float] = None, inplace: bool = False) -> pandas.DataFrame:
+    sos = filter_coeffs(critical_freqs, sampling_frequency, order, filter_type, band_type, cheby_param)
+    out = sos_filter(_channel_major(signal_df), sos, zero_lag=zero_lag)
+    return _like(signal_df, inplace, out.T.cpu().numpy())
+
+
+def linear_envelope(signal_df: pandas.DataFrame, critical_freqs, sampling_frequency: int, order: int,
+                    filter_type: str = "butter", zero_lag: bool = True, cheby_param: Optional[float] = None,
+                    zero_center_: bool = True, inplace: bool = False) -> pandas.DataFrame:
+    sos = filter_coeffs(critical_freqs, sampling_frequency, order, filter_type, "lowpass", cheby_param)
+    x = _channel_major(signal_df)
+    out = sos_filter(x, sos, zero_lag=zero_lag, mean=channel_means(x) if zero_center_ else None, rectify=True)
+    return _like(signal_df, inplace, out.T.cpu().numpy())
 
 
 def rms(signal_df: pandas.DataFrame, window_size: Union[int, float], inplace: bool = False,
