@@ -12,6 +12,7 @@ there is no CPU fallback.
 __version__ = "0.1.0"
 
 from .analysis import SynergyRunResult, find_synergies, nmf_mu_batched, vaf  # noqa: F401
+from .cache import load_trial, load_vicon_file_cached, save_trial  # noqa: F401
 from .emg import (  # noqa: F401
     digital_filter,
     envelope_windows,
@@ -50,6 +51,9 @@ __all__ = (
     # extensions
     "nmf_mu_batched",
     "envelope_windows",
+    "save_trial",
+    "load_trial",
+    "load_vicon_file_cached",
     "trial_synergies",
     "synergies_for_files",
 )
