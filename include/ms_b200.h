@@ -94,6 +94,12 @@ int64_t ms_workspace_masks_offset(int64_t n_bytes);
 int ms_scan(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, int64_t workspace_bytes,
             ms_scan_summary* d_summary, void* stream);
 
+/* Copies up to max_bytes bytes that follow blank row `which` of a finished ms_scan (the header lines of
+ * the next section, reader.py:250-835 parses them on the host) to d_out, and {offset, count} to d_info
+ * ({-1, 0} when that blank row was not reported): the host then needs one transfer, not two. */
+int ms_peek_after_blank(const uint8_t* d_bytes, int64_t n_bytes, const ms_scan_summary* d_summary, int32_t which,
+                        uint8_t* d_out, int32_t max_bytes, int64_t* d_info, void* stream);
+
 /* Rescan for buffers whose DATA rows contain '"' (ms_scan counted more quotes than the header
  * lines hold): same outputs, but commas and line ends inside quoted fields (csv excel dialect,
  * load_csv.py:30) are not delimiters.  Call after ms_scan, same buffer and workspace. */

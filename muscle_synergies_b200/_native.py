@@ -63,6 +63,7 @@ def _declare(L):
         "ms_workspace_masks_offset": (i64, [i64]),
         "ms_scan": (ctypes.c_int, [vp, i64, vp, i64, vp, vp]),
         "ms_scan_quoted": (ctypes.c_int, [vp, i64, vp, i64, vp, vp]),
+        "ms_peek_after_blank": (ctypes.c_int, [vp, i64, vp, i32, vp, i32, vp, vp]),
         "ms_parse": (ctypes.c_int, [vp, i64, vp, ctypes.POINTER(Section), i32, vp, vp]),
         "ms_transitions_workspace_bytes": (i64, [i64]),
         "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),

@@ -1076,6 +1076,35 @@ extern "C" int ms_scan_quoted(const uint8_t* d_bytes, int64_t n_bytes, void* d_w
     return ms_scan_impl(d_bytes, n_bytes, d_workspace, workspace_bytes, d_summary, stream, true);
 }
 
+// The header lines of the second section start right after the first blank row, a position only the
+// device knows when ms_scan finishes: this copies the bytes that follow it next to the summary, so
+// the host gets summary and header text in one device->host transfer instead of two round trips.
+__global__ void ms_peek_kernel(const uint8_t* __restrict__ src, int64_t n, const ms_scan_summary* __restrict__ summary,
+                               int which, uint8_t* __restrict__ out, int max_bytes, int64_t* __restrict__ info) {
+    int64_t from = -1, count = 0;
+    if ((uint32_t)which < summary->n_reported && summary->blank_end[which] >= 0) {
+        from = summary->blank_end[which] + 1;
+        if (from > n) from = n;
+        count = n - from < (int64_t)max_bytes ? n - from : (int64_t)max_bytes;
+    }
+    for (int64_t i = threadIdx.x; i < count; i += blockDim.x) out[i] = src[from + i];
+    if (threadIdx.x == 0) {
+        info[0] = from;
+        info[1] = count;
+    }
+}
+
+extern "C" int ms_peek_after_blank(const uint8_t* d_bytes, int64_t n_bytes, const ms_scan_summary* d_summary,
+                                   int32_t which, uint8_t* d_out, int32_t max_bytes, int64_t* d_info, void* stream) {
+    if (!d_bytes || !d_summary || !d_out || !d_info || n_bytes < 0 || max_bytes < 0 || which < 0 ||
+        which >= MS_MAX_BLANK_ROWS)
+        return MS_E_INVALID;
+    ms_peek_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_bytes, n_bytes, d_summary, which, d_out, max_bytes, d_info);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}
+
 extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
                         int32_t n_sections, uint64_t* d_status, void* stream) {
     if (!d_bytes || !d_workspace || !d_status || n_bytes < 0) return MS_E_INVALID;

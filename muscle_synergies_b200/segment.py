@@ -114,8 +114,9 @@ def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments
     return idx
 
 
-def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequence[int]) -> Segments:
-    """_organize_transitions (segment.py:787-917): 40 indices -> 4 trechos x 2 cycles x 4 phases."""
+def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequence[int], to_framesubfr_many=None) -> Segments:
+    """_organize_transitions (segment.py:787-917): 40 indices -> 4 trechos x 2 cycles x 4 phases.
+    `to_framesubfr_many`, when given, converts all 64 bounds in one call (same checks, same results)."""
 
     def single_leg_phase_type(pos: int) -> Phase:
         flags = loaded[pos]
@@ -134,18 +135,21 @@ def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequ
             return [Phase.DAE, Phase.BL, Phase.DAA, Phase.AS]
         return [Phase.DAA, Phase.AS, Phase.DAE, Phase.BL]
 
-    def cycle_dict(names, bounds):
-        slices = [slice(to_framesubfr(bounds[i]), to_framesubfr(bounds[i + 1] - 1)) for i in range(len(bounds) - 1)]
-        return OrderedDict(zip(names, slices))
+    # phase i of a trecho runs from bounds[i] to bounds[i + 1] - 1 (both converted to (frame, subframe))
+    all_bounds = [list(transitions[10 * n + 1 : 10 * n + 10]) for n in range(len(Trecho))]
+    wanted = [idx for bounds in all_bounds for i in range(8) for idx in (bounds[i], bounds[i + 1] - 1)]
+    if to_framesubfr_many is not None:
+        converted = iter(to_framesubfr_many(wanted))
+    else:
+        converted = iter([to_framesubfr(idx) for idx in wanted])
 
     segments = {}
     for n, trecho in enumerate(Trecho):
-        starts = list(transitions[10 * n + 1 : 10 * n + 9])
-        end = transitions[10 * n + 9]
         names = phase_seq(single_leg_phase_type(10 * n + 2), trecho)
+        slices = [slice(next(converted), next(converted)) for _ in range(8)]
         segments[trecho] = {
-            Cycle.FIRST: cycle_dict(names, starts[:5]),
-            Cycle.SECOND: cycle_dict(names, starts[4:] + [end]),
+            Cycle.FIRST: OrderedDict(zip(names, slices[:4])),
+            Cycle.SECOND: OrderedDict(zip(names, slices[4:])),
         }
     return segments
 
@@ -159,7 +163,8 @@ class Segmenter:
         self.transitions, self._loaded = transition_indices(
             _fz_tensor(left_fp), _fz_tensor(right_fp), min_phase_size, num_segments, with_loaded=True
         )
-        self._segments = organize_transitions(left_fp.to_framesubfr, self.transitions, self._loaded)
+        self._segments = organize_transitions(left_fp.to_framesubfr, self.transitions, self._loaded,
+                                              getattr(left_fp, "to_framesubfr_many", None))
 
     # ---- reference API ------------------------------------------------------------------------
     def ith_phase(self, trecho: Union[Trecho, int], i: int) -> Phase:
@@ -243,6 +248,9 @@ class Segmenter:
 
         Returns a list of (n_columns, n_rows_w) float64 CUDA tensors (channel-major), the
         same rows `device.df.iloc[device.to_index(w)]` selects (exclusive stop)."""
+        if all(w.step is None and w.start is not None and w.stop is not None for w in windows):
+            flat = device.to_index_many([b for w in windows for b in (w.start, w.stop)])
+            return cut_windows(device, [slice(flat[2 * i], flat[2 * i + 1]) for i in range(len(windows))])
         return cut_windows(device, [device.to_index(w) for w in windows])
 
 

@@ -10,7 +10,7 @@ exceptions.  Differences, all additive:
     memory layout pandas itself ends up with for the reference (user_data.py:396).
 """
 from functools import lru_cache
-from typing import Optional, Sequence, Tuple, Union
+from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import pandas as pd
@@ -203,6 +203,25 @@ class _SectionFrameTracker:
         self._validate_index_arg(index)
         return self._to_framesubfr(index)
 
+    # ---- batch forms (extension): same checks and results as a loop over the scalar methods, without
+    # the per-call overhead - the windowing stage converts 64 bounds per trial on its critical path
+    def to_framesubfr_many(self, indices: Sequence[int]) -> List[FrameSubfr]:
+        final = self.final_index
+        for index in indices:
+            if not 0 <= index <= final or index != int(index):
+                self._validate_index_arg(index)  # raises the scalar method's IndexError
+        return [self._to_framesubfr(index) for index in indices]
+
+    def to_index_many(self, pairs: Sequence[FrameSubfr]) -> List[int]:
+        frames, subs = self.num_frames, self.num_subframes
+        out = []
+        for pair in pairs:
+            frame, sub = pair
+            if not (1 <= frame <= frames and 0 <= sub < subs) or frame != int(frame) or sub != int(sub):
+                self._validate_framesubfr_args(pair)
+            out.append(self._to_index(pair))
+        return out
+
     def _validate_index_arg(self, index: int):
         if index not in range(self.final_index + 1):
             raise IndexError(f"index {index} out of bounds (max is self.final_index)")
@@ -345,6 +364,12 @@ class DeviceData:
 
     def to_framesubfr(self, index):
         return self._frame_tracker.to_framesubfr(index)
+
+    def to_framesubfr_many(self, indices):
+        return self._frame_tracker.to_framesubfr_many(indices)
+
+    def to_index_many(self, pairs):
+        return self._frame_tracker.to_index_many(pairs)
 
     def to_index(self, frame, subframe: Optional[int] = None):
         return self._frame_tracker.to_index(frame, subframe)

@@ -45,6 +45,7 @@ from .header import (
 
 _TERMINATOR = re.compile(rb"\r\n|\r|\n")
 _HEADER_LINES = 5
+_PEEK = 1 << 13  # bytes of header text fetched with the scan summary; take_lines' first window
 _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 
@@ -67,6 +68,7 @@ class _Source:
         self.d_bytes = d_bytes
         self.n = n
         self.host = host
+        self.windows = []  # (offset, bytes) pieces that came back with the scan summary
 
     def fetch(self, offset: int, length: int) -> bytes:
         offset = max(0, offset)
@@ -75,11 +77,14 @@ class _Source:
             return b""
         if self.host is not None:
             return self.host[offset:end].tobytes()
+        for w_off, w_bytes in self.windows:
+            if w_off <= offset and end <= w_off + len(w_bytes):
+                return w_bytes[offset - w_off : end - w_off]
         return self.d_bytes[offset:end].cpu().numpy().tobytes()
 
     def take_lines(self, offset: int, k: int) -> Tuple[bytes, int]:
         """Bytes of the first k physical lines starting at `offset` (fewer at EOF)."""
-        window = 1 << 13
+        window = _PEEK
         while True:
             chunk = self.fetch(offset, window)
             ends = []
@@ -131,6 +136,9 @@ class ViconLoader:
         self.lib = nat.lib()
         self._pinned = None
         self._pinned_summary = torch.empty(ctypes.sizeof(nat.ScanSummary) + 8, dtype=torch.uint8, pin_memory=True)
+        # header text that travels with the summary: [0, PEEK) of the file, then {offset, count} and the PEEK bytes
+        # after the first blank row (ms_peek_after_blank)
+        self._pinned_peek = torch.empty(2 * _PEEK + 16, dtype=torch.uint8, pin_memory=True)
 
     # ---- public -----------------------------------------------------------------------------
     def load_file(self, csv_filename) -> ViconNexusData:
@@ -210,8 +218,24 @@ class ViconLoader:
             d_summary = torch.empty(ctypes.sizeof(nat.ScanSummary), dtype=torch.uint8, device=self.device)
             nat.check(entry(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary.data_ptr(), sptr), what)
             self._pinned_summary[: d_summary.numel()].copy_(d_summary, non_blocking=True)
+            peek = src.host is None and src.n > 0
+            if peek:
+                # both sections' header lines come back with the summary (one wait instead of three)
+                k0 = min(src.n, _PEEK)
+                self._pinned_peek[:k0].copy_(src.d_bytes[:k0], non_blocking=True)
+                d_peek = torch.empty(_PEEK + 16, dtype=torch.uint8, device=self.device)
+                nat.check(self.lib.ms_peek_after_blank(src.d_bytes.data_ptr(), src.n, d_summary.data_ptr(), 0,
+                                                       d_peek.data_ptr() + 16, _PEEK, d_peek.data_ptr(), sptr),
+                          "ms_peek_after_blank")
+                self._pinned_peek[_PEEK:].copy_(d_peek, non_blocking=True)
         stream.synchronize()
         summary = nat.ScanSummary.from_buffer_copy(self._pinned_summary.numpy()[: d_summary.numel()].tobytes())
+        if peek:
+            host = self._pinned_peek.numpy()
+            src.windows = [(0, host[:k0].tobytes())]
+            off2, cnt2 = (int(v) for v in host[_PEEK : _PEEK + 16].view(np.int64))
+            if off2 >= 0 and cnt2 > 0:
+                src.windows.append((off2, host[_PEEK + 16 : _PEEK + 16 + cnt2].tobytes()))
         return summary, ws
 
     def _run(self, src: _Source, name: str) -> ViconNexusData:
@@ -250,14 +274,22 @@ class ViconLoader:
             )
             h_status = self._pinned_summary[-8:].view(torch.int64)
             h_status.copy_(d_status, non_blocking=True)
+        # the objects are built while the kernel runs; errors keep the reference's order: a bad data
+        # row first (raised while reading), the builder's complaints last (user_data.py:310-433)
+        data, build_error = None, None
+        try:
+            data = _build(plan, blocks)
+            data.blocks = [b for b in blocks if b is not None]  # the per-section HBM blocks (extension)
+        except (TypeError, ValueError, KeyError) as exc:
+            build_error = exc
         stream.synchronize()
         key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
         if key != nat.MS_ERR_NONE:
             _raise_device_error(src, plan, key, name, ws)
         if plan.deferred_error is not None:
             raise plan.deferred_error
-        data = _build(plan, blocks)
-        data.blocks = [b for b in blocks if b is not None]  # the per-section HBM blocks (extension)
+        if build_error is not None:
+            raise build_error
         return data
 
     def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2, return_exceptions: bool = False):
