@@ -309,9 +309,11 @@ def run_ours(args):
     torch.cuda.synchronize()
 
     def step_resident():
-        data = loader.load_device(d_bytes, n=n, name=layout)
-        seg = Segmenter(data)
-        cuts = Segmenter.cut(data.emg, [w[3] for w in seg.all_phase_windows()])
+        # one submission: parse, transition search and the gather of the 32 EMG phase windows are queued
+        # back to back; the parse status, the transitions and the window bounds come back in one wait
+        data = loader.load_device(d_bytes, n=n, name=layout, defer_check=True)
+        seg = Segmenter(data, cut_phases_of=(data.emg,))
+        cuts = seg.phase_cuts(data.emg)
         return data, cuts
 
     # shapes for the algorithmic byte count: B_alg = B_csv + 8 * N_kept

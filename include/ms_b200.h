@@ -125,6 +125,18 @@ int ms_find_transitions(const double* d_left_fz, const double* d_right_fz, int64
                         int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded,
                         int32_t* d_n_found, void* stream);
 
+/* Row ranges of the 32 phase windows (cycles == 0; order: trecho, cycle, phase) or the 8 cycle windows
+ * (cycles != 0) of one device, from transitions still in device memory (the output of
+ * ms_find_transitions with num_segments >= 40), so that ms_cut_windows can be queued without a host
+ * round trip: start = t_j / divisor, stop = (t_next - 1) / divisor, the values
+ * DeviceData.to_index(Segmenter.get_times_of(...)) yields (segment.py:862-917, user_data.py:513-661);
+ * divisor = 1 for force plates / EMG, num_subframes for trajectory markers.  Writes starts, stops
+ * (n_windows each) and offsets (n_windows + 1 prefix sums of len * n_channels).  All windows are
+ * empty when fewer than num_segments transitions were found. */
+int ms_plan_phase_windows(const int64_t* d_transitions, const int32_t* d_n_found, int32_t num_segments,
+                          int32_t cycles, int64_t divisor, int64_t n_rows, int32_t n_channels, int64_t* d_starts,
+                          int64_t* d_stops, int64_t* d_offsets, void* stream);
+
 /* DeviceData.__getitem__(slice) (user_data.py:727-731) for many windows at once: copies rows
  * [start_w, stop_w) of every channel of a channel-major array (d_src[c * src_stride + row])
  * to d_out[out_offset_w + c * (stop_w - start_w) + r].  max_window_len: the longest window

@@ -68,6 +68,7 @@ def _declare(L):
         "ms_transitions_workspace_bytes": (i64, [i64]),
         "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),
         "ms_cut_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp]),
+        "ms_plan_phase_windows": (ctypes.c_int, [vp, vp, i32, i32, i64, i64, i32, vp, vp, vp, vp]),
         "ms_channel_means": (ctypes.c_int, [vp, i64, i32, i64, vp, vp]),
         "ms_rms_envelope": (ctypes.c_int, [vp, i64, i32, i64, vp, i32, vp, i64, vp]),
         "ms_sosfilt_workspace_bytes": (ctypes.c_size_t, [i64, i32, i64, i32]),

@@ -596,7 +596,9 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
 //
 // Rows are processed in batches of PARSE_ROWS_CAP per section, so pathological inputs
 // (thousands of tiny rows in a tile) only cost more rounds.
+#ifndef PARSE_THREADS
 #define PARSE_THREADS 512
+#endif
 #define PARSE_WARPS (PARSE_THREADS / 32)
 #define PARSE_REGION (MS_TILE_BYTES + MS_MAX_ROW_BYTES)  // bytes staged per CTA
 #define PARSE_CHUNK (PARSE_REGION / PARSE_THREADS)        // 112 bytes per thread
@@ -680,6 +682,8 @@ __device__ __forceinline__ uint32_t ms_load4(const uint8_t* __restrict__ reg, in
     return __funnelshift_r(w[0], w[1], (p & 3) << 3);
 }
 
+__constant__ uint32_t ms_pow10_u32[5] = {1u, 10u, 100u, 1000u, 10000u};
+
 // Value of four ASCII-digit bytes already reduced to 0..9 (first character most significant).
 __device__ __forceinline__ uint32_t ms_digits4(uint32_t t) {
     const uint32_t v = (t * 10u + (t >> 8)) & 0x00ff00ffu;  // two-digit values in bytes 0 and 2
@@ -697,15 +701,14 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
                                               unsigned long long* status, int64_t t0) {
     const int fs = *pp;
     int p = fs;
-    uint32_t x = ms_load4(reg, p);
-    unsigned c = x & 0xffu;
+    unsigned c = reg[p];
     uint64_t bits = MS_NAN_BITS;
     if (!ms_is_delim(c)) {
-        uint64_t sign = 0;
-        if (c == '-') {
-            sign = 0x8000000000000000ull;
-            x = ms_load4(reg, ++p);
-        }
+        // the sign costs no branch: one byte decides where the digits' first word starts
+        const bool neg = c == '-';
+        const uint64_t sign = neg ? 0x8000000000000000ull : 0ull;
+        p += neg ? 1 : 0;
+        uint32_t x = ms_load4(reg, p);
         uint64_t acc = 0;
         int ndig = 0, nfrac = 0;
         bool dot = false;
@@ -733,28 +736,21 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
             }
         }
 #endif
+        // One loop body for whole and partial words (a full word is the j == 4 case), so the lanes of a
+        // warp - same column, different digit counts - stay on one path and differ only in trip count.
         for (;;) {
             const uint32_t t = x ^ 0x30303030u;
             const uint32_t nd = ((t + 0x76767676u) | t) & 0x80808080u;  // bytes that are not digits
-            if (nd == 0) {
-                acc = acc * 10000ull + ms_digits4(t);
-                ndig += 4;
-                nfrac += dot ? 4 : 0;
-                p += 4;
+            const int j = nd ? (__ffs(nd) - 1) >> 3 : 4;                // leading digits in this word: 0..4
+            acc = acc * ms_pow10_u32[j] + ms_digits4((uint32_t)((uint64_t)t << ((4 - j) << 3)));
+            ndig += j;
+            nfrac += dot ? j : 0;
+            c = (uint32_t)((uint64_t)x >> (j << 3)) & 0xffu;  // 0 when j == 4
+            const bool isdot = c == '.' && !dot;
+            p += j + (isdot ? 1 : 0);
+            if (j == 4 || isdot) {
+                dot = dot || isdot;
                 x = ms_load4(reg, p);
-                continue;
-            }
-            const int j = (__ffs(nd) - 1) >> 3;  // digits before the first other byte: 0..3
-            if (j) {
-                acc = acc * (j == 1 ? 10ull : j == 2 ? 100ull : 1000ull) + ms_digits4(t << ((4 - j) << 3));
-                ndig += j;
-                nfrac += dot ? j : 0;
-            }
-            c = (x >> (j << 3)) & 0xffu;
-            p += j;
-            if (c == '.' && !dot) {
-                dot = true;
-                x = ms_load4(reg, ++p);
                 continue;
             }
             break;
@@ -787,10 +783,11 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         }
         if (ok && ms_is_delim(c) && (unsigned)(ex + 22) <= 44u) {
             double v;
-            if (ex >= 0) {
-                v = (double)acc * ms_pow10_double[ex];
-            } else if ((acc >> 32) == 0) {
+            if (ex <= 0 && (acc >> 32) == 0) {
+                // integers (ex == 0) take the same path as fractions: a / 1 is exact there too
                 v = ms_div_pow10_u32((uint32_t)acc, -ex);  // exact, division-free (exhaustively verified)
+            } else if (ex >= 0) {
+                v = (double)acc * ms_pow10_double[ex];
             } else {
                 v = (double)acc / ms_pow10_double[-ex];
             }

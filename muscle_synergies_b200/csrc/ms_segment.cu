@@ -141,3 +141,51 @@ extern "C" int ms_cut_windows(const double* d_src, int64_t src_stride, int32_t n
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
 }
+
+// ---------------------------------------------------------------------------------------------------
+// The 32 phase windows (or 8 cycle windows) of a trial as row ranges of one device, computed ON the GPU from
+// the transitions still in device memory, so the gather can be queued behind the search without a host
+// round trip.  Same arithmetic as the host path: phase i of trecho k runs from transition 10k+1+i to
+// transition 10k+2+i minus one (_organize_transitions, segment.py:862-917), both converted to (frame,
+// subframe) and back by the device's own tracker (user_data.py:513-661), then used as df.iloc[a:b]:
+//   a = t_j / divisor, b = (t_{j+1} - 1) / divisor      divisor = 1 for the force plate / EMG section,
+//                                                        num_subframes for trajectory markers.
+__global__ void ms_plan_phase_windows_kernel(const int64_t* __restrict__ transitions, const int32_t* __restrict__ n_found,
+                                             int num_segments, int cycles, int64_t divisor, int64_t n_rows, int n_channels,
+                                             int64_t* __restrict__ starts, int64_t* __restrict__ stops,
+                                             int64_t* __restrict__ offsets) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const int per_trecho = cycles ? 2 : 8, span = cycles ? 4 : 1, n_windows = 4 * per_trecho;
+    const bool ok = *n_found >= num_segments && num_segments >= 40;
+    int64_t off = 0;
+    for (int w = 0; w < n_windows; w++) {
+        int64_t a = 0, b = 0;
+        if (ok) {
+            const int j = 10 * (w / per_trecho) + 1 + (w % per_trecho) * span;
+            a = transitions[j] / divisor;
+            b = (transitions[j + span] - 1) / divisor;
+            a = a < 0 ? 0 : (a > n_rows ? n_rows : a);
+            b = b < a ? a : (b > n_rows ? n_rows : b);
+        }
+        starts[w] = a;
+        stops[w] = b;
+        offsets[w] = off;
+        off += (b - a) * n_channels;
+    }
+    offsets[n_windows] = off;
+}
+
+extern "C" int ms_plan_phase_windows(const int64_t* d_transitions, const int32_t* d_n_found, int32_t num_segments,
+                                     int32_t cycles, int64_t divisor, int64_t n_rows, int32_t n_channels,
+                                     int64_t* d_starts, int64_t* d_stops, int64_t* d_offsets, void* stream) {
+    if (!d_transitions || !d_n_found || !d_starts || !d_stops || !d_offsets || divisor < 1 || n_rows < 0 ||
+        n_channels < 0)
+        return MS_E_INVALID;
+    ms_plan_phase_windows_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(d_transitions, d_n_found, num_segments, cycles,
+                                                                     divisor, n_rows, n_channels, d_starts, d_stops,
+                                                                     d_offsets);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}
+

@@ -66,6 +66,62 @@ def _fz_tensor(dev: DeviceData):
     return dev.tensor[coords.index("Fz")]
 
 
+class _TransitionSearch:
+    """ms_find_transitions queued on the current stream; `finish()` waits and reads the result.
+    `extra_words` int64 slots follow the results in the same buffer (`extra`), so that work queued
+    behind the search can return its own small outputs in the same device->host copy."""
+
+    def __init__(self, left_fz, right_fz, min_phase_size: int, num_segments: int, extra_words: int = 0):
+        import torch
+
+        lib = nat.lib()
+        if not (left_fz.is_cuda and right_fz.is_cuda):
+            raise nat.NativeError("transition_indices needs CUDA tensors; there is no CPU fallback")
+        left_fz = left_fz.contiguous()
+        right_fz = right_fz.contiguous()
+        if left_fz.dtype != torch.float64 or right_fz.dtype != torch.float64 or left_fz.shape != right_fz.shape:
+            raise ValueError("left/right reactions must be float64 vectors of equal length")
+        n = int(left_fz.numel())
+        dev = left_fz.device
+        self.min_phase_size, self.num_segments = min_phase_size, num_segments
+        self.want = want = num_segments if num_segments > 0 else max(1, n)
+        work = torch.empty(int(lib.ms_transitions_workspace_bytes(n)), dtype=torch.uint8, device=dev)
+        # one result buffer -> one device->host copy: [indices (int64) | loaded flags, count (int32) | extra]
+        self.tail_words = (want + 2 + 1) // 2
+        self.res = torch.empty(want + self.tail_words + extra_words, dtype=torch.int64, device=dev)
+        self.d_transitions = self.res[:want]
+        tail = self.res[want : want + self.tail_words].view(torch.int32)
+        loaded, self.d_found = tail[:want], tail[want : want + 1]
+        self.extra = self.res[want + self.tail_words :]
+        self.stream = torch.cuda.current_stream(dev)
+        nat.check(
+            lib.ms_find_transitions(
+                left_fz.data_ptr(), right_fz.data_ptr(), n, int(min_phase_size), int(want), work.data_ptr(),
+                self.d_transitions.data_ptr(), loaded.data_ptr(), self.d_found.data_ptr(),
+                ctypes.c_void_p(self.stream.cuda_stream),
+            ),
+            "ms_find_transitions",
+        )
+        self._keep = (left_fz, right_fz, work)
+
+    def finish(self):
+        """(indices, loaded flags, extra words as a host int64 tensor); raises like the reference when
+        fewer than num_segments transitions exist."""
+        import torch
+
+        want = self.want
+        host = self.res.cpu()
+        tail = host[want : want + self.tail_words].view(torch.int32)
+        k = int(tail[want].item())
+        if self.num_segments > 0 and k < self.num_segments:
+            legs = 1 if k % 2 == 0 else 2
+            raise ValueError(
+                f"no phase found with {self.min_phase_size} adjacent measurements with {legs} leg(s) with a nonzero reaction"
+                f" (found {k} of {self.num_segments} transitions)"
+            )
+        return host[:k].tolist(), tail[:k].tolist(), host[want + self.tail_words :]
+
+
 def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments: int = 40, with_loaded=False):
     """_transition_indices (segment.py:667-755) on two CUDA float64 vectors.
 
@@ -73,42 +129,7 @@ def transition_indices(left_fz, right_fz, min_phase_size: int = 10, num_segments
     bit 0 left, bit 1 right).  Raises ValueError when fewer than num_segments exist
     (num_segments=0 keeps the reference meaning "as many as there are").
     """
-    import torch
-
-    lib = nat.lib()
-    if not (left_fz.is_cuda and right_fz.is_cuda):
-        raise nat.NativeError("transition_indices needs CUDA tensors; there is no CPU fallback")
-    left_fz = left_fz.contiguous()
-    right_fz = right_fz.contiguous()
-    if left_fz.dtype != torch.float64 or right_fz.dtype != torch.float64 or left_fz.shape != right_fz.shape:
-        raise ValueError("left/right reactions must be float64 vectors of equal length")
-    n = int(left_fz.numel())
-    dev = left_fz.device
-    want = num_segments if num_segments > 0 else max(1, n)
-    work = torch.empty(int(lib.ms_transitions_workspace_bytes(n)), dtype=torch.uint8, device=dev)
-    # one result buffer -> one device->host copy: [indices (int64) | loaded flags, count (int32)]
-    res = torch.empty(want + (want + 2 + 1) // 2, dtype=torch.int64, device=dev)
-    out = res[:want]
-    tail = res[want:].view(torch.int32)
-    loaded, found = tail[:want], tail[want : want + 1]
-    stream = torch.cuda.current_stream(dev)
-    nat.check(
-        lib.ms_find_transitions(
-            left_fz.data_ptr(), right_fz.data_ptr(), n, int(min_phase_size), int(want), work.data_ptr(),
-            out.data_ptr(), loaded.data_ptr(), found.data_ptr(), ctypes.c_void_p(stream.cuda_stream),
-        ),
-        "ms_find_transitions",
-    )
-    host = res.cpu()
-    k = int(host[want:].view(torch.int32)[want].item())
-    if num_segments > 0 and k < num_segments:
-        legs = 1 if k % 2 == 0 else 2
-        raise ValueError(
-            f"no phase found with {min_phase_size} adjacent measurements with {legs} leg(s) with a nonzero reaction"
-            f" (found {k} of {num_segments} transitions)"
-        )
-    idx = host[:k].tolist()
-    loaded_host = host[want:].view(torch.int32)[:k].tolist()
+    idx, loaded_host, _ = _TransitionSearch(left_fz, right_fz, min_phase_size, num_segments).finish()
     if with_loaded:
         return idx, loaded_host
     return idx
@@ -154,17 +175,78 @@ def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequ
     return segments
 
 
+_PLAN_WORDS = 32 + 32 + 33  # starts, stops, offsets of the 32 phase windows of one device
+
+
 class Segmenter:
     """Segments a trial into trechos, cycles and phases from the two force plates."""
 
-    def __init__(self, data: ViconNexusData, min_phase_size: int = 10, num_segments: int = 40):
+    def __init__(self, data: ViconNexusData, min_phase_size: int = 10, num_segments: int = 40, cut_phases_of=()):
+        """`cut_phases_of` (extension): devices of `data` whose 32 phase windows are gathered on the GPU
+        in the same submission as the transition search (no host round trip in between); read them
+        with `phase_cuts(device)`.  A trial loaded with `defer_check=True` is checked here."""
         left_fp, right_fp = data.forcepl  # exactly two plates, like reactions()
         self._data = data
-        self.transitions, self._loaded = transition_indices(
-            _fz_tensor(left_fp), _fz_tensor(right_fp), min_phase_size, num_segments, with_loaded=True
-        )
+        precut = list(cut_phases_of)
+        if precut and num_segments < 40:
+            raise ValueError("cut_phases_of needs the full 40 transitions")
+        search = _TransitionSearch(_fz_tensor(left_fp), _fz_tensor(right_fp), min_phase_size, num_segments,
+                                   extra_words=_PLAN_WORDS * len(precut))
+        queued = [self._queue_phase_cuts(search, dev, i, left_fp) for i, dev in enumerate(precut)]
+        try:
+            self.transitions, self._loaded, extra = search.finish()
+        finally:
+            check = getattr(data, "check", None)
+            if check is not None:
+                check()  # a parse error of a deferred load comes first, as it would have at load time
         self._segments = organize_transitions(left_fp.to_framesubfr, self.transitions, self._loaded,
                                               getattr(left_fp, "to_framesubfr_many", None))
+        self._phase_cuts = {}
+        for i, (dev, out) in enumerate(queued):
+            self._phase_cuts[id(dev)] = (dev, self._finish_phase_cuts(dev, out, extra[i * _PLAN_WORDS : (i + 1) * _PLAN_WORDS]))
+
+    def _queue_phase_cuts(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData):
+        """Plans (on the device) and gathers the 32 phase windows of `dev` behind the search."""
+        import torch
+
+        lib = nat.lib()
+        src = dev.tensor
+        n_ch, n_rows = int(src.shape[0]), int(src.shape[1])
+        same_section = type(dev._frame_tracker) is type(plate._frame_tracker)
+        divisor = 1 if same_section else plate._frame_tracker.num_subframes
+        meta = search.extra[slot * _PLAN_WORDS : (slot + 1) * _PLAN_WORDS]
+        starts, stops, offsets = meta[:32], meta[32:64], meta[64:97]
+        out = torch.empty(max(1, n_ch * n_rows), dtype=torch.float64, device=src.device)  # upper bound: every row once
+        sptr = ctypes.c_void_p(search.stream.cuda_stream)
+        nat.check(lib.ms_plan_phase_windows(search.d_transitions.data_ptr(), search.d_found.data_ptr(), search.want, 0,
+                                            divisor, n_rows, n_ch, starts.data_ptr(), stops.data_ptr(),
+                                            offsets.data_ptr(), sptr), "ms_plan_phase_windows")
+        if n_ch:
+            nat.check(lib.ms_cut_windows(src.data_ptr(), int(src.stride(0)), n_ch, starts.data_ptr(), stops.data_ptr(),
+                                         offsets.data_ptr(), 32, out.data_ptr(), n_rows, sptr), "ms_cut_windows")
+        return dev, out
+
+    def _finish_phase_cuts(self, dev: DeviceData, out, meta):
+        meta = meta.tolist()
+        starts, stops, offsets = meta[:32], meta[32:64], meta[64:97]
+        # the device planned the row ranges; the host path must agree (and raises what it would raise)
+        windows = [w[3] for w in self.all_phase_windows()]
+        flat = dev.to_index_many([b for w in windows for b in (w.start, w.stop)])
+        n_rows = int(dev.tensor.shape[1])
+        for i in range(32):
+            a = min(flat[2 * i], n_rows)
+            if (starts[i], stops[i]) != (a, max(a, min(flat[2 * i + 1], n_rows))):
+                raise AssertionError("device-planned phase window differs from the host's")
+        n_ch = int(dev.tensor.shape[0])
+        return [out[offsets[i] : offsets[i + 1]].view(n_ch, stops[i] - starts[i]) for i in range(32)]
+
+    def phase_cuts(self, device: DeviceData):
+        """The 32 phase windows of `device` (order of `all_phase_windows`) as (n_columns, n_rows_w) CUDA
+        tensors: the ones gathered at construction (`cut_phases_of`), else gathered now."""
+        hit = self._phase_cuts.get(id(device))
+        if hit is not None:
+            return hit[1]
+        return Segmenter.cut(device, [w[3] for w in self.all_phase_windows()])
 
     # ---- reference API ------------------------------------------------------------------------
     def ith_phase(self, trecho: Union[Trecho, int], i: int) -> Phase:

@@ -71,6 +71,13 @@ class ViconNexusData:
         self.emg = emg
         self.traj = traj
 
+    def check(self) -> None:
+        """Raises what loading this trial raised on the device, if it was loaded with
+        `defer_check=True` and not checked yet (extension; a no-op otherwise)."""
+        pending, self._pending_check = getattr(self, "_pending_check", None), None
+        if pending is not None:
+            pending()
+
     def __getitem__(self, device_type: Union[DeviceType, str]):
         device_type = self._parse_device_type(device_type)
         if device_type is DeviceType.FORCE_PLATE:

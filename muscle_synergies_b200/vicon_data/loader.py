@@ -169,16 +169,21 @@ class ViconLoader:
             staging.numpy()[:n] = host
         return self._load_host(host, staging, name)
 
-    def load_device(self, d_bytes, n: Optional[int] = None, name: str = "<device bytes>", host=None) -> ViconNexusData:
+    def load_device(self, d_bytes, n: Optional[int] = None, name: str = "<device bytes>", host=None,
+                    defer_check: bool = False) -> ViconNexusData:
         """CSV bytes already in HBM.  The tensor must be readable 16 bytes past `n` rounded up
-        to 16 (allocate it with `padded_size(n)`)."""
+        to 16 (allocate it with `padded_size(n)`).
+
+        defer_check (extension): return as soon as the parse kernel is queued; whatever the data rows
+        would have raised is raised by `data.check()` instead - which `Segmenter(data)` calls after its
+        own wait - so that a load followed by device-side work costs one host wait less."""
         n = int(d_bytes.numel() if n is None else n)
         if d_bytes.numel() < _pad16(n):
             torch = self.torch
             padded = torch.empty(_pad16(n), dtype=torch.uint8, device=self.device)
             padded[:n].copy_(d_bytes[:n])
             d_bytes = padded
-        return self._run(_Source(d_bytes, n, host), name)
+        return self._run(_Source(d_bytes, n, host), name, defer_check)
 
     @staticmethod
     def padded_size(n: int) -> int:
@@ -238,7 +243,7 @@ class ViconLoader:
                 src.windows.append((off2, host[_PEEK + 16 : _PEEK + 16 + cnt2].tobytes()))
         return summary, ws
 
-    def _run(self, src: _Source, name: str) -> ViconNexusData:
+    def _run(self, src: _Source, name: str, defer_check: bool = False) -> ViconNexusData:
         torch = self.torch
         summary, ws = self._scan(src)
         try:
@@ -272,8 +277,13 @@ class ViconLoader:
                 self.lib.ms_parse(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), sections, n_sec, d_status.data_ptr(), sptr),
                 "ms_parse",
             )
-            h_status = self._pinned_summary[-8:].view(torch.int64)
+            if defer_check:
+                h_status = torch.empty(1, dtype=torch.int64, pin_memory=True)  # outlives this call
+            else:
+                h_status = self._pinned_summary[-8:].view(torch.int64)
             h_status.copy_(d_status, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(stream)
         # the objects are built while the kernel runs; errors keep the reference's order: a bad data
         # row first (raised while reading), the builder's complaints last (user_data.py:310-433)
         data, build_error = None, None
@@ -282,14 +292,21 @@ class ViconLoader:
             data.blocks = [b for b in blocks if b is not None]  # the per-section HBM blocks (extension)
         except (TypeError, ValueError, KeyError) as exc:
             build_error = exc
-        stream.synchronize()
-        key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
-        if key != nat.MS_ERR_NONE:
-            _raise_device_error(src, plan, key, name, ws)
-        if plan.deferred_error is not None:
-            raise plan.deferred_error
-        if build_error is not None:
-            raise build_error
+
+        def check():
+            copied.synchronize()
+            key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
+            if key != nat.MS_ERR_NONE:
+                _raise_device_error(src, plan, key, name, ws)
+            if plan.deferred_error is not None:
+                raise plan.deferred_error
+            if build_error is not None:
+                raise build_error
+
+        if defer_check and data is not None:
+            data._pending_check = check
+            return data
+        check()
         return data
 
     def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2, return_exceptions: bool = False):

@@ -145,3 +145,60 @@ def test_full_size_trial_segments(ms):
         for sl, cut in zip(slices, cuts):
             a, b = so.window_rows(section, tuple(sl.start), tuple(sl.stop), n_sub)
             assert torch.equal(cut.view(torch.int64), dev.tensor[:, a:b].contiguous().view(torch.int64))
+
+
+def test_fused_submission_equals_step_by_step(ms, d_trial):
+    """defer_check + cut_phases_of (one host wait) against the three-step path, EMG and a marker."""
+    import torch
+
+    from muscle_synergies_b200.segment import Segmenter
+    from tools.synth_vicon import synth_layout
+
+    blob = synth_layout("D", seed=0)
+    loader = ms.ViconLoader()
+    d = torch.empty(loader.padded_size(blob.nbytes), dtype=torch.uint8, device="cuda")
+    d[: blob.nbytes].copy_(torch.from_numpy(blob))
+    data = loader.load_device(d, n=blob.nbytes, name="D", defer_check=True)
+    seg = Segmenter(data, cut_phases_of=(data.emg, data.traj[3], data.forcepl[1]))
+    ref = Segmenter(d_trial)
+    assert seg.transitions == ref.transitions
+    windows = [w[3] for w in ref.all_phase_windows()]
+    assert [w[3] for w in seg.all_phase_windows()] == windows
+    for fused_dev, plain_dev in ((data.emg, d_trial.emg), (data.traj[3], d_trial.traj[3]), (data.forcepl[1], d_trial.forcepl[1])):
+        got = seg.phase_cuts(fused_dev)
+        want = Segmenter.cut(plain_dev, windows)
+        assert len(got) == len(want) == 32
+        for g, w in zip(got, want):
+            assert g.shape == w.shape
+            assert torch.equal(g.view(torch.int64), w.view(torch.int64))
+    # a device that was not pre-cut is gathered on demand
+    later = seg.phase_cuts(data.traj[0])
+    assert all(torch.equal(a.view(torch.int64), b.view(torch.int64)) for a, b in zip(later, Segmenter.cut(d_trial.traj[0], windows)))
+
+
+def test_deferred_check_raises_the_load_error(ms):
+    import torch
+
+    from muscle_synergies_b200.segment import Segmenter
+    from tools.synth_vicon import synth_layout
+
+    blob = synth_layout("D", seed=0).copy()
+    text = blob.tobytes()
+    pos = text.index(b"\r\n", 40_000) + 2  # start of a data row well inside the Devices section
+    comma = text.index(b",", text.index(b",", pos) + 1) + 1
+    bad = bytearray(text)
+    bad[comma : comma + 1] = b"x"
+    loader = ms.ViconLoader()
+    d = torch.empty(loader.padded_size(len(bad)), dtype=torch.uint8, device="cuda")
+    d[: len(bad)].copy_(torch.frombuffer(bad, dtype=torch.uint8))
+    with pytest.raises(RuntimeError, match="error parsing line") as eager:
+        loader.load_device(d, n=len(bad), name="bad.csv")
+    data = loader.load_device(d, n=len(bad), name="bad.csv", defer_check=True)  # nothing raised yet
+    with pytest.raises(RuntimeError) as deferred:
+        data.check()
+    assert str(deferred.value) == str(eager.value)
+    data.check()  # reported once
+    data = loader.load_device(d, n=len(bad), name="bad.csv", defer_check=True)
+    with pytest.raises(RuntimeError) as via_segmenter:
+        Segmenter(data)
+    assert str(via_segmenter.value) == str(eager.value)
