@@ -61,35 +61,87 @@ struct MsNmfArgs {
     float* vaf_out;  // [m + 1] of this problem
 };
 
+// Shared-memory layout of one problem (floats; every row 16-byte aligned so that rows are read as float4):
+//   sX   [n][XS]   X, columns padded with zeros to MP = roundup(m, 4); XS = MP or MP + 4 so that XS / 4 is odd
+//                  (a quarter warp reading one float4 per row then touches 8 different bank groups)
+//   sW   [n][WS]   W, columns padded with zeros to KP = roundup(K, 4); WS likewise
+//   sHt  [MP][KP]  H transposed (rows past m are zero): the K weights of muscle j are one or more float4 (W step, residual)
+//   sH   [K][MP]   H (H step, H H^T)
+//   sHHt [K][KP], sWtW [KP][KP], sWtX [KP][MP], sPart [slices][tiles * 16], s_red [32]
+__host__ __device__ inline int ms_nmf_pad4(int v) { return (v + 3) & ~3; }
+__host__ __device__ inline int ms_nmf_stride(int padded) { return ((padded >> 2) & 1) ? padded : padded + 4; }
+
+// element e of the 4 x 4 tile list (W^T W tiles, then W^T X tiles) -> its place in sWtW / sWtX
+template <int K>
+__device__ __forceinline__ float* ms_nmf_tile_dst(int e, int MQ, int MP, float* sWtW, float* sWtX) {
+    constexpr int KP = (K + 3) & ~3, KQ = KP / 4;
+    const int tile = e >> 4, r = (e >> 2) & 3, c = e & 3;
+    if (tile < KQ * KQ) return sWtW + (4 * (tile / KQ) + r) * KP + 4 * (tile % KQ) + c;
+    const int q = tile - KQ * KQ;
+    return sWtX + (4 * (q / MQ) + r) * MP + 4 * (q % MQ) + c;
+}
+
 template <int K>
 __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* sm) {
+    constexpr int KP = (K + 3) & ~3, KQ = KP / 4;
+    constexpr int WS = ((KP >> 2) & 1) ? KP : KP + 4;
     const int n = A.n, m = A.m;
-    const int xs = m | 1;  // odd row strides: consecutive rows hit different banks
-    constexpr int ws = K | 1;
-    float* sX = sm;                // [n][xs]
-    float* sW = sX + n * xs;       // [n][ws]
-    float* sH = sW + n * ws;       // [K][m]
-    float* sHHt = sH + K * m;      // [K][K]
-    float* sWtW = sHHt + K * K;    // [K][K]
-    float* sWtX = sWtW + K * K;    // [K][m]   (contiguous with sWtW)
-    float* s_red = sWtX + K * m;   // [32]
+    const int MP = ms_nmf_pad4(m), MQ = MP / 4, XS = ms_nmf_stride(MP);
+    const int n_tiles = KQ * KQ + KQ * MQ;  // 4 x 4 output tiles of W^T W and W^T X
+    int slices = NMF_THREADS / n_tiles;     // row slices that work on the tiles side by side
+    if (slices < 1) slices = 1;
+    if (slices > n) slices = n;
+    float* sX = sm;
+    float* sW = sX + n * XS;
+    float* sHt = sW + n * WS;
+    float* sH = sHt + MP * KP;
+    float* sHHt = sH + K * MP;
+    float* sWtW = sHHt + K * KP;
+    float* sWtX = sWtW + KP * KP;
+    float* sPart = sWtX + KP * MP;
+    float* s_red = sPart + NMF_THREADS * 16;
     const int tid = threadIdx.x;
 
-    for (int i = tid; i < n * m; i += NMF_THREADS) sX[(i / m) * xs + (i % m)] = A.X[i];
-    for (int i = tid; i < n * K; i += NMF_THREADS) sW[(i / K) * ws + (i % K)] = A.Wp[i];
-    for (int i = tid; i < K * m; i += NMF_THREADS) sH[i] = A.Hp[i];
+    for (int i = tid; i < n * XS; i += NMF_THREADS) {
+        const int r = i / XS, c = i - r * XS;
+        sX[i] = c < m ? A.X[r * m + c] : 0.f;
+    }
+    for (int i = tid; i < n * WS; i += NMF_THREADS) {
+        const int r = i / WS, c = i - r * WS;
+        sW[i] = c < K ? A.Wp[r * K + c] : 0.f;
+    }
+    for (int i = tid; i < K * MP; i += NMF_THREADS) {
+        const int a = i / MP, j = i - a * MP;
+        sH[i] = j < m ? A.Hp[a * m + j] : 0.f;
+    }
+    for (int i = tid; i < MP * KP; i += NMF_THREADS) {
+        const int j = i / KP, a = i - j * KP;
+        sHt[i] = (a < K && j < m) ? A.Hp[a * m + j] : 0.f;
+    }
+    // the padding of H H^T must read as zero: the W step runs over whole float4 groups of components
+    for (int i = tid; i < K * KP; i += NMF_THREADS) sHHt[i] = 0.f;
     __syncthreads();
 
+    // sum over the rows this thread owns of |x_i - w_i H|^2
     auto residual_sq = [&]() {
         float acc = 0.f;
         for (int i = tid; i < n; i += NMF_THREADS) {
-            float w[K];
+            float w[KP];
 #pragma unroll
-            for (int c = 0; c < K; c++) w[c] = sW[i * ws + c];
+            for (int q = 0; q < KQ; q++) {
+                const float4 v = *reinterpret_cast<const float4*>(sW + i * WS + 4 * q);
+                w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
+            }
             for (int j = 0; j < m; j++) {
-                float r = sX[i * xs + j];
+                float r = sX[i * XS + j];
 #pragma unroll
-                for (int c = 0; c < K; c++) r = fmaf(-w[c], sH[c * m + j], r);
+                for (int q = 0; q < KQ; q++) {
+                    const float4 h = *reinterpret_cast<const float4*>(sHt + j * KP + 4 * q);
+                    r = fmaf(-w[4 * q], h.x, r);
+                    r = fmaf(-w[4 * q + 1], h.y, r);
+                    r = fmaf(-w[4 * q + 2], h.z, r);
+                    r = fmaf(-w[4 * q + 3], h.w, r);
+                }
                 acc = fmaf(r, r, acc);
             }
         }
@@ -98,9 +150,18 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     auto compute_hht = [&]() {
         for (int e = tid; e < K * K; e += NMF_THREADS) {
             const int a = e / K, b = e % K;
-            float acc = 0.f;
-            for (int j = 0; j < m; j++) acc = fmaf(sH[a * m + j], sH[b * m + j], acc);
-            sHHt[e] = acc;
+            // rows of H as float4 (the zero padding adds nothing), two accumulators
+            float acc0 = 0.f, acc1 = 0.f;
+            for (int jq = 0; jq < MQ; jq++) {
+                const float4 u = *reinterpret_cast<const float4*>(sH + a * MP + 4 * jq);
+                const float4 v = *reinterpret_cast<const float4*>(sH + b * MP + 4 * jq);
+                acc0 = fmaf(u.x, v.x, acc0);
+                acc1 = fmaf(u.y, v.y, acc1);
+                acc0 = fmaf(u.z, v.z, acc0);
+                acc1 = fmaf(u.w, v.w, acc1);
+            }
+            const float acc = acc0 + acc1;
+            sHHt[a * KP + b] = acc;
         }
     };
 
@@ -112,51 +173,114 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     compute_hht();
     __syncthreads();
 
+    // index arithmetic that does not change from one iteration to the next
+    const bool t2_active = tid < n_tiles * slices;
+    const float* t2_left = sW;   // 4 columns of W
+    const float* t2_right = sW;  // 4 columns of W (tile of W^T W) or of X (tile of W^T X)
+    int t2_rstride = WS, t2_i0 = 0, t2_i1 = 0;
+    float* t2_part = sPart;
+    if (t2_active) {
+        const int tile = tid % n_tiles, sl = tid / n_tiles;
+        const int rows_per = (n + slices - 1) / slices;
+        t2_i0 = sl * rows_per;
+        t2_i1 = min(n, t2_i0 + rows_per);
+        if (tile < KQ * KQ) {
+            t2_left = sW + 4 * (tile / KQ);
+            t2_right = sW + 4 * (tile % KQ);
+        } else {
+            const int q = tile - KQ * KQ;
+            t2_left = sW + 4 * (q / MQ);
+            t2_right = sX + 4 * (q % MQ);
+            t2_rstride = XS;
+        }
+        t2_part = sPart + (sl * n_tiles + tile) * 16;
+    }
+    // where this thread's first reduced tile element goes (usually its only one)
+    float* t2_dst0 = ms_nmf_tile_dst<K>(min(tid, n_tiles * 16 - 1), MQ, MP, sWtW, sWtX);
+
     int it = 0;
     for (it = 1; it <= A.max_iter; it++) {
-        // ---- W <- W * (X H^T) / (W (H H^T)); zero the accumulators of the H step meanwhile
-        for (int e = tid; e < K * K + K * m; e += NMF_THREADS) sWtW[e] = 0.f;
+        // ---- W <- W * (X H^T) / (W (H H^T)): one row per thread, H^T and H H^T read as broadcast float4
         for (int i = tid; i < n; i += NMF_THREADS) {
-            float w[K], num[K];
+            float w[KP], num[KP], den[KP];
 #pragma unroll
-            for (int c = 0; c < K; c++) {
-                w[c] = sW[i * ws + c];
-                num[c] = 0.f;
-            }
-            for (int j = 0; j < m; j++) {
-                const float x = sX[i * xs + j];
-#pragma unroll
-                for (int c = 0; c < K; c++) num[c] = fmaf(x, sH[c * m + j], num[c]);
+            for (int q = 0; q < KQ; q++) {
+                const float4 v = *reinterpret_cast<const float4*>(sW + i * WS + 4 * q);
+                w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
             }
 #pragma unroll
-            for (int c = 0; c < K; c++) {
-                float den = 0.f;
+            for (int c = 0; c < KP; c++) num[c] = den[c] = 0.f;
+            for (int jq = 0; jq < MQ; jq++) {
+                const float4 xv = *reinterpret_cast<const float4*>(sX + i * XS + 4 * jq);
+                const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                for (int b = 0; b < K; b++) den = fmaf(w[b], sHHt[b * K + c], den);
-                if (den == 0.f) den = NMF_EPS;
-                sW[i * ws + c] = w[c] * (num[c] / den);
+                for (int jj = 0; jj < 4; jj++) {
+                    const float* ht = sHt + (4 * jq + jj) * KP;  // rows past m exist and are zero, like x there
+#pragma unroll
+                    for (int q = 0; q < KQ; q++) {
+                        const float4 h = *reinterpret_cast<const float4*>(ht + 4 * q);
+                        num[4 * q] = fmaf(x4[jj], h.x, num[4 * q]);
+                        num[4 * q + 1] = fmaf(x4[jj], h.y, num[4 * q + 1]);
+                        num[4 * q + 2] = fmaf(x4[jj], h.z, num[4 * q + 2]);
+                        num[4 * q + 3] = fmaf(x4[jj], h.w, num[4 * q + 3]);
+                    }
+                }
             }
+#pragma unroll
+            for (int b = 0; b < K; b++) {
+#pragma unroll
+                for (int q = 0; q < KQ; q++) {
+                    const float4 g = *reinterpret_cast<const float4*>(sHHt + b * KP + 4 * q);
+                    den[4 * q] = fmaf(w[b], g.x, den[4 * q]);
+                    den[4 * q + 1] = fmaf(w[b], g.y, den[4 * q + 1]);
+                    den[4 * q + 2] = fmaf(w[b], g.z, den[4 * q + 2]);
+                    den[4 * q + 3] = fmaf(w[b], g.w, den[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < KP; c++) {
+                const float d = den[c] == 0.f ? NMF_EPS : den[c];
+                w[c] = w[c] * (num[c] / d);  // padding components: 0 * (0 / eps) = 0
+            }
+#pragma unroll
+            for (int q = 0; q < KQ; q++)
+                *reinterpret_cast<float4*>(sW + i * WS + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
         __syncthreads();
-        // ---- W^T W and W^T X: slices of rows per thread group, reduced with shared atomics
-        {
-            const int pairs = K * K + K * m;
-            int split = NMF_THREADS / pairs;
-            if (split < 1) split = 1;
-            const int rows_per = (n + split - 1) / split;
-            for (int e = tid; e < pairs * split; e += NMF_THREADS) {
-                const int pair = e % pairs, sl = e / pairs;
-                const int i0 = sl * rows_per, i1 = min(n, i0 + rows_per);
-                float acc = 0.f;
-                if (pair < K * K) {
-                    const int a = pair / K, b = pair % K;
-                    for (int i = i0; i < i1; i++) acc = fmaf(sW[i * ws + a], sW[i * ws + b], acc);
-                } else {
-                    const int q = pair - K * K, a = q / m, j = q % m;
-                    for (int i = i0; i < i1; i++) acc = fmaf(sW[i * ws + a], sX[i * xs + j], acc);
-                }
-                atomicAdd(&sWtW[pair], acc);
+        // ---- W^T W and W^T X: 4 x 4 register tiles, the rows split into slices that run side by side
+        if (t2_active) {
+            float acc[4][4];
+#pragma unroll
+            for (int r = 0; r < 4; r++)
+#pragma unroll
+                for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+#pragma unroll 2
+            for (int i = t2_i0; i < t2_i1; i++) {
+                const float4 a = *reinterpret_cast<const float4*>(t2_left + i * WS);
+                const float4 b = *reinterpret_cast<const float4*>(t2_right + i * t2_rstride);
+                const float av[4] = {a.x, a.y, a.z, a.w}, bv[4] = {b.x, b.y, b.z, b.w};
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = fmaf(av[r], bv[c], acc[r][c]);
             }
+#pragma unroll
+            for (int r = 0; r < 4; r++) *reinterpret_cast<float4*>(t2_part + 4 * r) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
+        }
+        __syncthreads();
+        for (int e = tid; e < n_tiles * 16; e += NMF_THREADS) {
+            // four independent partial sums: the loads of a dependent chain would each wait for the last add
+            float a0 = 0.f, a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            const int stride = n_tiles * 16;
+            int sl = 0;
+            for (; sl + 4 <= slices; sl += 4) {
+                a0 += sPart[sl * stride + e];
+                a1 += sPart[(sl + 1) * stride + e];
+                a2 += sPart[(sl + 2) * stride + e];
+                a3 += sPart[(sl + 3) * stride + e];
+            }
+            for (; sl < slices; sl++) a0 += sPart[sl * stride + e];
+            *(e == tid ? t2_dst0 : ms_nmf_tile_dst<K>(e, MQ, MP, sWtW, sWtX)) = (a0 + a1) + (a2 + a3);
         }
         __syncthreads();
         // ---- H <- H * (W^T X) / ((W^T W) H)
@@ -164,16 +288,20 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
             float newh[(NMF_MAX_K * NMF_MAX_M + NMF_THREADS - 1) / NMF_THREADS];
             int q = 0;
             for (int e = tid; e < K * m; e += NMF_THREADS, q++) {
-                const int a = e / m, j = e % m;
+                const int a = e / m, j = e - a * m;
                 float den = 0.f;
 #pragma unroll
-                for (int b = 0; b < K; b++) den = fmaf(sWtW[a * K + b], sH[b * m + j], den);
+                for (int b = 0; b < K; b++) den = fmaf(sWtW[a * KP + b], sH[b * MP + j], den);
                 if (den == 0.f) den = NMF_EPS;
-                newh[q] = sH[e] * (sWtX[e] / den);
+                newh[q] = sH[a * MP + j] * (sWtX[a * MP + j] / den);
             }
             __syncthreads();
             q = 0;
-            for (int e = tid; e < K * m; e += NMF_THREADS, q++) sH[e] = newh[q];
+            for (int e = tid; e < K * m; e += NMF_THREADS, q++) {
+                const int a = e / m, j = e - a * m;
+                sH[a * MP + j] = newh[q];
+                sHt[j * KP + a] = newh[q];
+            }
         }
         __syncthreads();
         compute_hht();
@@ -187,12 +315,12 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     if (it > A.max_iter) it = A.max_iter;
 
     // ---- results: factors, ||X - W H||_F, variance accounted for (analysis.py:642-667)
-    for (int i = tid; i < n * K; i += NMF_THREADS) A.Wp[i] = sW[(i / K) * ws + (i % K)];
-    for (int i = tid; i < K * m; i += NMF_THREADS) A.Hp[i] = sH[i];
+    for (int i = tid; i < n * K; i += NMF_THREADS) A.Wp[i] = sW[(i / K) * WS + (i % K)];
+    for (int i = tid; i < K * m; i += NMF_THREADS) A.Hp[i] = sH[(i / m) * MP + (i % m)];
     const float res = residual_sq();
     float xx = 0.f;
     for (int i = tid; i < n * m; i += NMF_THREADS) {
-        const float v = sX[(i / m) * xs + (i % m)];
+        const float v = sX[(i / m) * XS + (i % m)];
         xx = fmaf(v, v, xx);
     }
     xx = ms_block_sum(xx, s_red);
@@ -205,10 +333,10 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     for (int j = tid; j < m; j += NMF_THREADS) {
         float rs = 0.f, cs = 0.f;
         for (int i = 0; i < n; i++) {
-            float r = sX[i * xs + j];
+            float r = sX[i * XS + j];
             cs = fmaf(r, r, cs);
 #pragma unroll
-            for (int c = 0; c < K; c++) r = fmaf(-sW[i * ws + c], sH[c * m + j], r);
+            for (int c = 0; c < K; c++) r = fmaf(-sW[i * WS + c], sH[c * MP + j], r);
             rs = fmaf(r, r, rs);
         }
         A.vaf_out[1 + j] = 1.f - rs / cs;
@@ -247,17 +375,24 @@ __global__ void __launch_bounds__(NMF_THREADS)
     }
 }
 
+static size_t ms_nmf_resident_fixed_floats(int m, int kmax) {
+    const int KP = ms_nmf_pad4(kmax), MP = ms_nmf_pad4(m);
+    return (size_t)MP * KP + (size_t)kmax * MP + (size_t)kmax * KP + (size_t)KP * KP + (size_t)KP * MP +
+           (size_t)NMF_THREADS * 16 + 32;
+}
+static size_t ms_nmf_resident_row_floats(int m, int kmax) {
+    return (size_t)ms_nmf_stride(ms_nmf_pad4(m)) + (size_t)ms_nmf_stride(ms_nmf_pad4(kmax));
+}
 static size_t ms_nmf_resident_smem(int n, int m, int kmax) {
-    const int xs = m | 1, ws = kmax | 1;
-    return sizeof(float) * ((size_t)n * xs + (size_t)n * ws + 2 * (size_t)kmax * m + 2 * (size_t)kmax * kmax + 32);
+    return sizeof(float) * ((size_t)n * ms_nmf_resident_row_floats(m, kmax) + ms_nmf_resident_fixed_floats(m, kmax));
 }
 
 // Largest n the resident kernel takes for (m, kmax); 0 if the shape is unsupported.
 extern "C" int32_t ms_nmf_resident_max_rows(int32_t m, int32_t kmax) {
     if (m < 1 || m > NMF_MAX_M || kmax < 1 || kmax > NMF_MAX_K) return 0;
     const size_t budget = 227 * 1024 - 1024;
-    const size_t fixed = sizeof(float) * (2 * (size_t)kmax * m + 2 * (size_t)kmax * kmax + 32);
-    const size_t per_row = sizeof(float) * ((size_t)(m | 1) + (size_t)(kmax | 1));
+    const size_t fixed = sizeof(float) * ms_nmf_resident_fixed_floats(m, kmax);
+    const size_t per_row = sizeof(float) * ms_nmf_resident_row_floats(m, kmax);
     return (int32_t)((budget - fixed) / per_row);
 }
 

@@ -14,8 +14,8 @@ n = blob.nbytes
 d = torch.empty(loader.padded_size(n), dtype=torch.uint8, device="cuda")
 d[:n].copy_(torch.from_numpy(blob))
 for _ in range(reps):
-    data = loader.load_device(d, n=n, name=layout)
-    seg = Segmenter(data)
-    cuts = Segmenter.cut(data.emg, [w[3] for w in seg.all_phase_windows()])
+    data = loader.load_device(d, n=n, name=layout, defer_check=True)
+    seg = Segmenter(data, cut_phases_of=(data.emg,))
+    cuts = seg.phase_cuts(data.emg)
 torch.cuda.synchronize()
 print("done", layout, n)
