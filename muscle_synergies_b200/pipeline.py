@@ -15,6 +15,7 @@ then every cycle is resampled and amplitude-normalised - `emg.envelope_windows`)
 cycles x ranks x restarts run as ONE launch of the batched NMF kernel on the device-resident
 envelopes.  This module is an extension: the reference has no batch entry point.
 """
+from collections.abc import Mapping
 from dataclasses import dataclass, field
 from typing import Dict, Iterable, List, Optional, Sequence, Tuple
 
@@ -27,6 +28,25 @@ from .segment import Cycle, Segmenter, Trecho
 from .vicon_data import ViconLoader, ViconNexusData
 
 
+class _Frames(Mapping):
+    """rank -> DataFrame, built from the array on first access (a trial has 64 of these; building
+    them eagerly costs more host time than the GPU spends on the whole trial)."""
+
+    def __init__(self, arrays: Dict[int, np.ndarray], columns):
+        self._arrays, self._columns, self._frames = arrays, columns, {}
+
+    def __getitem__(self, k):
+        if k not in self._frames:
+            self._frames[k] = pandas.DataFrame(self._arrays[k].astype(np.float64), columns=self._columns)
+        return self._frames[k]
+
+    def __iter__(self):
+        return iter(self._arrays)
+
+    def __len__(self):
+        return len(self._arrays)
+
+
 @dataclass
 class CycleSynergies:
     """Synergies of one gait cycle: per rank, the restart with the smallest reconstruction error."""
@@ -34,20 +54,37 @@ class CycleSynergies:
     trecho: Trecho
     cycle: Cycle
     window: slice  # (frame, subframe) slice, as Segmenter.get_times_of returns it
-    vaf_values: pandas.DataFrame  # index: rank; columns: "All signals" + muscles  (analysis.py:884-894)
-    components: Dict[int, pandas.DataFrame]  # rank -> (rank x muscles) synergy vectors
+    components: Mapping  # rank -> (rank x muscles) DataFrame of synergy vectors
     transformed: Dict[int, np.ndarray]  # rank -> (reduce_to x rank) activations
     n_iter: Dict[int, int]
     reconstruction_err: Dict[int, float]
     random_state: Dict[int, int]
+    _vaf: np.ndarray = field(repr=False, default=None)  # (ranks, 1 + muscles)
+    _labels: list = field(repr=False, default=None)
+    _vaf_frame: Optional[pandas.DataFrame] = field(repr=False, default=None)
+
+    @property
+    def vaf_values(self) -> pandas.DataFrame:
+        """index: rank; columns: "All signals" + muscles (the table of analysis.py:884-894)."""
+        if self._vaf_frame is None:
+            self._vaf_frame = pandas.DataFrame(self._vaf, columns=self._labels, index=np.array(list(self.components)))
+        return self._vaf_frame
 
 
 @dataclass
 class TrialSynergies:
     cycles: List[CycleSynergies]
-    restarts: pandas.DataFrame  # one row per (trecho, cycle, rank, restart): seed, n_iter, err, overall VAF
     envelopes: object = field(repr=False, default=None)  # (n_cycles, reduce_to, muscles) float64 CUDA tensor
     batch: Optional[NMFBatchResult] = field(repr=False, default=None)
+    _restart_columns: dict = field(repr=False, default=None)
+    _restarts: Optional[pandas.DataFrame] = field(repr=False, default=None)
+
+    @property
+    def restarts(self) -> pandas.DataFrame:
+        """One row per (trecho, cycle, rank, restart): seed, n_iter, reconstruction error, overall VAF."""
+        if self._restarts is None:
+            self._restarts = pandas.DataFrame(self._restart_columns)
+        return self._restarts
 
     def __getitem__(self, key: Tuple[Trecho, Cycle]) -> CycleSynergies:
         trecho, cycle = Segmenter._parse_trecho(key[0]), Segmenter._parse_cycle(key[1])
@@ -93,12 +130,12 @@ def trial_synergies(data: ViconNexusData, min_components: int = 1, max_component
         for ki, k in enumerate(sweep):
             p = (ci * n_k + ki) * n_restarts + int(best[ci, ki])
             rows.append(res.vaf[p].astype(np.float64))
-            comps[k] = pandas.DataFrame(res.H[p].astype(np.float64), columns=muscles)
+            comps[k] = res.H[p]
             acts[k] = res.W[p].astype(np.float64)
             iters[k], errs[k], rstate[k] = int(res.n_iter[p]), float(res.err[p]), int(res.seeds[p])
-        vaf_values = pandas.DataFrame(np.array(rows), columns=labels, index=np.array(sweep))
-        cycles.append(CycleSynergies(trecho, cycle, window, vaf_values, comps, acts, iters, errs, rstate))
-    restarts = pandas.DataFrame({
+        cycles.append(CycleSynergies(trecho, cycle, window, _Frames(comps, muscles), acts, iters, errs, rstate,
+                                     np.array(rows), labels))
+    restart_columns = {
         "trecho": np.repeat([t.value for (t, _, _) in wins], n_k * n_restarts),
         "cycle": np.repeat([c.value for (_, c, _) in wins], n_k * n_restarts),
         "n_components": ranks,
@@ -106,8 +143,8 @@ def trial_synergies(data: ViconNexusData, min_components: int = 1, max_component
         "n_iter": res.n_iter,
         "reconstruction_err": res.err.astype(np.float64),
         "All signals": res.vaf[:, 0].astype(np.float64),
-    })
-    return TrialSynergies(cycles, restarts, env, res if keep_batch else None)
+    }
+    return TrialSynergies(cycles, env, res if keep_batch else None, restart_columns)
 
 
 def synergies_for_files(paths: Sequence[str], loader: Optional[ViconLoader] = None, **kwargs) -> Iterable[Tuple[str, TrialSynergies]]:
