@@ -88,13 +88,116 @@ __global__ void __launch_bounds__(128)
     }
 }
 
+// Block version (windows that fit shared memory): a CTA owns RMS_SPAN consecutive outputs of one channel, stages
+// the squares of the RMS_SPAN + window - 1 samples they need with coalesced loads, turns them into prefix sums
+// in place (each thread scans a contiguous chunk, chunk totals are scanned across the block), and every output
+// is one difference of two prefix values - coalesced stores, a handful of shared-memory reads per output.
+// The prefix sums are kept as unevaluated pairs hi + lo (error-free TwoSum), so that the difference is as
+// accurate in a quiet stretch next to a burst as the direct window sum numpy computes.
+#define RMS_SPAN 4096
+#define RMS_THREADS 256
+struct MsDD {
+    double hi, lo;
+};
+__device__ __forceinline__ MsDD ms_dd_add(MsDD a, MsDD b) {
+    const double s = a.hi + b.hi;
+    const double bb = s - a.hi;
+    const double err = (a.hi - (s - bb)) + (b.hi - bb);
+    const double lo = (a.lo + b.lo) + err;
+    MsDD r;
+    r.hi = s + lo;
+    r.lo = lo - (r.hi - s);
+    return r;
+}
+__global__ void __launch_bounds__(RMS_THREADS)
+    ms_rms_block_kernel(const double* __restrict__ src, int64_t stride, int64_t n, const double* __restrict__ mean,
+                        int window, int chunk, double* __restrict__ out, int64_t out_stride) {
+    extern __shared__ double s_dyn[];  // hi[RMS_THREADS * chunk], lo[RMS_THREADS * chunk]
+    __shared__ MsDD s_warp[RMS_THREADS / 32];
+    const int c = blockIdx.y, tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const double mu = mean ? mean[c] : 0.0;
+    const double* __restrict__ x = src + (int64_t)c * stride;
+    const int h = (window - 1) / 2;
+    const int64_t o0 = (int64_t)blockIdx.x * RMS_SPAN;       // first output of this CTA
+    const int64_t in0 = o0 - (window - 1 - h);               // first sample it needs
+    const int need = RMS_SPAN + window - 1, total = RMS_THREADS * chunk;  // total >= need
+    double* s_hi = s_dyn;
+    double* s_lo = s_dyn + total;
+    for (int k = tid; k < total; k += RMS_THREADS) {
+        const int64_t g = in0 + k;
+        double v = 0.0;
+        if (k < need && g >= 0 && g < n) {
+            v = x[g] - mu;
+            v *= v;
+        }
+        s_hi[k] = v;
+    }
+    __syncthreads();
+    // inclusive scan of this thread's chunk, in place
+    MsDD run = {0.0, 0.0};
+    double* mine_hi = s_hi + tid * chunk;
+    double* mine_lo = s_lo + tid * chunk;
+    for (int k = 0; k < chunk; k++) {
+        const MsDD v = {mine_hi[k], 0.0};
+        run = ms_dd_add(run, v);
+        mine_hi[k] = run.hi;
+        mine_lo[k] = run.lo;
+    }
+    // exclusive scan of the chunk totals across the block
+    MsDD inc = run;
+    for (int o = 1; o < 32; o <<= 1) {
+        MsDD t;
+        t.hi = __shfl_up_sync(0xffffffffu, inc.hi, o);
+        t.lo = __shfl_up_sync(0xffffffffu, inc.lo, o);
+        if (lane >= o) inc = ms_dd_add(t, inc);
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    // base = everything before this thread's chunk = (warps before) + (lanes before in this warp)
+    MsDD before = {__shfl_up_sync(0xffffffffu, inc.hi, 1), __shfl_up_sync(0xffffffffu, inc.lo, 1)};
+    if (lane == 0) before.hi = before.lo = 0.0;
+    MsDD base = {0.0, 0.0};
+    for (int w = 0; w < warp; w++) base = ms_dd_add(base, s_warp[w]);
+    base = ms_dd_add(base, before);
+    for (int k = 0; k < chunk; k++) {
+        const MsDD v = {mine_hi[k], mine_lo[k]};
+        const MsDD r = ms_dd_add(base, v);
+        mine_hi[k] = r.hi;
+        mine_lo[k] = r.lo;
+    }
+    __syncthreads();
+    // prefix k = sum of squares of samples in0 .. in0 + k; output o needs samples o - (window-1-h) .. o + h
+    const double inv = 1.0 / (double)window;
+    double* __restrict__ y = out + (int64_t)c * out_stride;
+    for (int k = tid; k < RMS_SPAN; k += RMS_THREADS) {
+        const int64_t o = o0 + k;
+        if (o >= n) break;
+        const int b = k + window - 1;
+        double sum = s_hi[b], low = s_lo[b];
+        if (k > 0) {
+            sum -= s_hi[k - 1];
+            low -= s_lo[k - 1];
+        }
+        y[o] = sqrt(fmax(sum + low, 0.0) * inv);
+    }
+}
+
 extern "C" int ms_rms_envelope(const double* d_src, int64_t stride, int32_t n_channels, int64_t n, const double* d_mean,
                                int32_t window, double* d_out, int64_t out_stride, void* stream) {
     if (!d_src || !d_out || n_channels < 1 || n < 1 || window < 1 || window > n) return MS_E_INVALID;
     cudaStream_t st = (cudaStream_t)stream;
-    const int64_t threads = (n + RMS_RUN - 1) / RMS_RUN;
-    ms_rms_kernel<<<dim3((unsigned)((threads + 127) / 128), n_channels), 128, 0, st>>>(d_src, stride, n, d_mean, window,
-                                                                                     d_out, out_stride);
+    int chunk = (RMS_SPAN + window - 1 + RMS_THREADS - 1) / RMS_THREADS;
+    chunk |= 1;  // odd chunk length: neighbouring threads' chunks start in different banks
+    const size_t smem = sizeof(double) * 2 * (size_t)RMS_THREADS * chunk;
+    if (smem <= 200 * 1024) {
+        MS_CUDA_CHECK(cudaFuncSetAttribute(ms_rms_block_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+        const dim3 grid((unsigned)((n + RMS_SPAN - 1) / RMS_SPAN), n_channels);
+        ms_rms_block_kernel<<<grid, RMS_THREADS, smem, st>>>(d_src, stride, n, d_mean, window, chunk, d_out, out_stride);
+    } else {  // very long windows: the running-sum kernel
+        const int64_t threads = (n + RMS_RUN - 1) / RMS_RUN;
+        ms_rms_kernel<<<dim3((unsigned)((threads + 127) / 128), n_channels), 128, 0, st>>>(d_src, stride, n, d_mean,
+                                                                                         window, d_out, out_stride);
+    }
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;

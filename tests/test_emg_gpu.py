@@ -28,6 +28,18 @@ def test_dataframe_level_functions(emg):
     for win in (1, 2, 7, 1000, 1001, 7001):
         np.testing.assert_allclose(emg.rms(df, win).to_numpy(), eo.rms(x, win), rtol=RTOL, atol=1e-13)
     np.testing.assert_allclose(emg.rms(df, 0.5, sampling_frequency=2000).to_numpy(), eo.rms(x, 1000), rtol=RTOL, atol=1e-13)
+    # spans several blocks of the shared-memory kernel; the last window is too long for it (running-sum kernel)
+    xl = rng.normal(0.002, 0.01, (60_000, 2))
+    dfl = pd.DataFrame(xl, columns=list("ab"))
+    for win in (3, 1000, 4097, 20_000, 30_000):
+        np.testing.assert_allclose(emg.rms(dfl, win).to_numpy(), eo.rms(xl, win), rtol=RTOL, atol=1e-13)
+    # a quiet stretch right after a burst: window sums a million times smaller than the running total
+    xb = np.concatenate([rng.normal(0, 1.0, (3000, 2)), rng.normal(0, 1e-3, (5000, 2))])
+    dfb = pd.DataFrame(xb, columns=list("ab"))
+    for win in (50, 1000):
+        got, want = emg.rms(dfb, win).to_numpy(), eo.rms(xb, win)
+        np.testing.assert_allclose(got[4200:], want[4200:], rtol=RTOL)  # relative, on the quiet part alone
+        np.testing.assert_allclose(got, want, rtol=RTOL, atol=1e-13)
     np.testing.assert_allclose(emg.normalize(df).to_numpy(), eo.normalize(x), rtol=RTOL)
     for r in (2, 200, 7001, 9000):
         got = emg.time_normalize(df, r)
