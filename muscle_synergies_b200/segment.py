@@ -175,6 +175,31 @@ def organize_transitions(to_framesubfr, transitions: Sequence[int], loaded: Sequ
     return segments
 
 
+class _WindowViews(Sequence):
+    """The gathered windows as a read-only sequence of (n_columns, n_rows_w) CUDA tensors: views of one
+    buffer, made when asked for (32 tensor objects per trial are host time the GPU would wait for)."""
+
+    def __init__(self, buffer, n_channels: int, starts, stops, offsets):
+        self._buffer, self._n_ch = buffer, n_channels
+        self._starts, self._stops, self._offsets = starts, stops, offsets
+        self._views = {}
+
+    def __len__(self):
+        return len(self._starts)
+
+    def __getitem__(self, i):
+        if isinstance(i, slice):
+            return [self[j] for j in range(*i.indices(len(self)))]
+        if i < 0:
+            i += len(self)
+        if not 0 <= i < len(self):
+            raise IndexError(i)
+        if i not in self._views:
+            self._views[i] = self._buffer[self._offsets[i] : self._offsets[i + 1]].view(
+                self._n_ch, self._stops[i] - self._starts[i])
+        return self._views[i]
+
+
 _PLAN_WORDS = 32 + 32 + 33  # starts, stops, offsets of the 32 phase windows of one device
 
 
@@ -237,8 +262,7 @@ class Segmenter:
             a = min(flat[2 * i], n_rows)
             if (starts[i], stops[i]) != (a, max(a, min(flat[2 * i + 1], n_rows))):
                 raise AssertionError("device-planned phase window differs from the host's")
-        n_ch = int(dev.tensor.shape[0])
-        return [out[offsets[i] : offsets[i + 1]].view(n_ch, stops[i] - starts[i]) for i in range(32)]
+        return _WindowViews(out, int(dev.tensor.shape[0]), starts, stops, offsets)
 
     def phase_cuts(self, device: DeviceData):
         """The 32 phase windows of `device` (order of `all_phase_windows`) as (n_columns, n_rows_w) CUDA

@@ -78,15 +78,21 @@ class SectionLayout:
     devices: List[DeviceLayout] = field(default_factory=list)
     num_cols: int = 0
     complete: bool = False  # all five header lines were seen
+    _n_keep: Optional[int] = field(default=None, repr=False, compare=False)
 
     @property
     def n_keep(self) -> int:
         """Channels the device stores: csv columns [2, 2 + n_keep)."""
+        if self.complete and self._n_keep is not None:
+            return self._n_keep  # a complete layout no longer changes (and is shared through the header cache)
         last = 1
         for dev in self.devices:
             if dev.last_col is not None:
                 last = max(last, min(dev.last_col, self.num_cols - 1))
-        return max(0, last - 1)
+        keep = max(0, last - 1)
+        if self.complete:
+            self._n_keep = keep
+        return keep
 
 
 class HeaderMachine:

@@ -15,9 +15,9 @@ d = torch.empty(loader.padded_size(n), dtype=torch.uint8, device="cuda")
 d[:n].copy_(torch.from_numpy(blob))
 
 def step():
-    data = loader.load_device(d, n=n, name=layout)
-    seg = Segmenter(data)
-    return Segmenter.cut(data.emg, [w[3] for w in seg.all_phase_windows()])
+    data = loader.load_device(d, n=n, name=layout, defer_check=True)
+    seg = Segmenter(data, cut_phases_of=(data.emg,))
+    return seg.phase_cuts(data.emg)
 
 for _ in range(5):
     step()
