@@ -281,6 +281,11 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the product has no CPU path")
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
+    # staging buffers and the threads that fill them next to the GPU (restored before the CPU baseline)
+    from muscle_synergies_b200.sharding import bind_to_gpu_numa
+
+    all_cpus = os.sched_getaffinity(0)
+    numa_cpus = bind_to_gpu_numa(local_rank)
     dist = None
     if world > 1:
         import torch.distributed as dist
@@ -435,6 +440,7 @@ def run_ours(args):
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
+        os.sched_setaffinity(0, all_cpus)
         gbs, cores, sample, _wall = cpu_baseline()
         cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
 
@@ -447,6 +453,7 @@ def run_ours(args):
                 "workload": WORKLOAD if layout == "T10" else layout, "csv_bytes_per_gpu": n, "kept_doubles_per_gpu": n_kept,
                 "l2": "input (CSV) and output are each larger than the 126 MB L2; no explicit flush",
                 "parallelism": f"{world} ranks, one trial per rank per step, no data-path collective",
+                "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,

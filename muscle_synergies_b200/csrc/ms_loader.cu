@@ -829,24 +829,41 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     if (!any) return;
 
     // ---- A1. stage [t0 - 16, t0 + REGION + 16) in shared memory; beyond the end: '\n'.
-    // Asynchronous 16-byte copies (cp.async, LDGSTS): they stay in flight while the masks are
-    // fetched and scanned below; the bytes are first needed for the ownership test.
-    for (int i = tid; i < PARSE_BYTES_SMEM / 16; i += PARSE_THREADS) {
-        const int64_t off = t0 - PARSE_PAD + (int64_t)i * 16;
-        uint8_t* dst = smem_raw + i * 16;
-        if (off >= 0 && off + 16 <= n) {
-            const uint32_t saddr = (uint32_t)__cvta_generic_to_shared(dst);
-            asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(saddr), "l"(src + off) : "memory");
-        } else {
-            uint4 v;
-            if (off < 0)
-                v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
-            else
-                v = ms_load16(src, off, n, 0x0a0a0a0au);
-            *reinterpret_cast<uint4*>(dst) = v;
+    // One bulk asynchronous copy (cp.async.bulk, the TMA engine: UBLKCP) issued by a single thread moves every
+    // whole 16-byte chunk that lies inside the buffer and reports to an mbarrier; it stays in flight while the
+    // masks are fetched and scanned below (the bytes are first needed for the ownership test).  The chunks at
+    // the edges of the file - before byte 0, or holding / beyond byte n - are filled by hand.
+    __shared__ __align__(8) unsigned long long s_stage_bar;
+    const int64_t off0 = t0 - PARSE_PAD;                                  // file offset of chunk 0
+    const int lo_chunk = off0 < 0 ? (int)((-off0) >> 4) : 0;              // first chunk inside the file
+    const int64_t whole = (n >> 4) - (off0 >> 4);                         // chunks that end at or before byte n
+    const int hi_chunk = (int)max((int64_t)lo_chunk, min((int64_t)(PARSE_BYTES_SMEM / 16), whole));
+    if (tid == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+        const uint32_t bytes = (uint32_t)(hi_chunk - lo_chunk) * 16u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        if (bytes) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_raw + lo_chunk * 16);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                         "l"(src + off0 + (int64_t)lo_chunk * 16), "r"(bytes), "r"(bar)
+                         : "memory");
         }
     }
-    asm volatile("cp.async.commit_group;\n" ::: "memory");
+    for (int i = tid; i < PARSE_BYTES_SMEM / 16; i += PARSE_THREADS) {
+        if (i >= lo_chunk && i < hi_chunk) {
+            if (lo_chunk == 0 && hi_chunk == PARSE_BYTES_SMEM / 16) break;  // the usual tile: nothing by hand
+            continue;
+        }
+        const int64_t off = off0 + (int64_t)i * 16;
+        uint4 v;
+        if (off < 0)
+            v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        else
+            v = ms_load16(src, off, n, 0x0a0a0a0au);
+        *reinterpret_cast<uint4*>(smem_raw + i * 16) = v;
+    }
 
     // ---- A2. delimiter masks of my chunk: classified once, by ms_scan_kernel
     const int c0 = tid * PARSE_CHUNK;
@@ -905,8 +922,20 @@ __global__ void __launch_bounds__(PARSE_THREADS, 3)
     if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
     __syncthreads();
 
-    // the staged bytes are needed from here on
-    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    // the staged bytes are needed from here on (the barrier above also made the mbarrier's init visible)
+    {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
     __syncthreads();
 
     // ---- ownership: rows that START in [t0, t0 + tile_len)

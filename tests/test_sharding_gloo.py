@@ -61,3 +61,11 @@ def test_world_size_2_gloo(tmp_path):
         s.bind(("127.0.0.1", 0))
         port = s.getsockname()[1]
     mp.spawn(_worker, args=(2, port, str(tmp_path)), nprocs=2, join=True)
+
+
+def test_cpulist_parsing():
+    from muscle_synergies_b200.sharding import parse_cpulist
+
+    assert parse_cpulist("0-3,8,10-11\n") == [0, 1, 2, 3, 8, 10, 11]
+    assert parse_cpulist("5") == [5]
+    assert parse_cpulist("") == []
