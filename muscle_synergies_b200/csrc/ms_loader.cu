@@ -713,25 +713,53 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
         int ndig = 0, nfrac = 0;
         bool dot = false;
 #ifndef MS_NO_SHAPE_SHORTCUTS
-        // Two shortcuts for the shapes that fill Vicon exports (same results as the loop below):
+        // Straight-line paths for the two shapes that fill Vicon exports (same results as the loop below).  Lanes
+        // of a warp parse the same column, so what matters is that they all stay on ONE path: a lane that leaves
+        // it makes the whole warp execute the general loop as well (which is why the first path runs to nine
+        // digits: stopping at eight left one lane in most warps behind and was slower than no shortcut at all).
         if ((x & 0xffffu) == 0x2e30u) {
-            // "0." - every EMG sample: skip the one-digit integer part
-            dot = true;
-            ndig = 1;
-            p += 2;
-            x = ms_load4(reg, p);
+            // "0." and 4 to 9 fraction digits, then the delimiter - every EMG sample ("0.0123456", "0.00123457",
+            // "0.000123457"): both digit words at once, 32-bit arithmetic, one exact scaling
+            const int pf = p + 2;
+            const uint32_t* w = reinterpret_cast<const uint32_t*>(reg) + (pf >> 2);
+            const int sh = (pf & 3) << 3;
+            const uint32_t w1 = w[1];
+            const uint32_t y0 = __funnelshift_r(w[0], w1, sh), y1 = __funnelshift_r(w1, w[2], sh);
+            const uint32_t u0 = y0 ^ 0x30303030u, u1 = y1 ^ 0x30303030u;
+            const uint32_t n0 = ((u0 + 0x76767676u) | u0) & 0x80808080u;
+            const uint32_t n1 = ((u1 + 0x76767676u) | u1) & 0x80808080u;
+            if (n0 == 0) {
+                const int j1 = n1 ? (__ffs(n1) - 1) >> 3 : 4;  // fraction digits in the second word
+                uint32_t frac = ms_digits4(u0) * ms_pow10_u32[j1] + ms_digits4((uint32_t)((uint64_t)u1 << ((4 - j1) << 3)));
+                int nf = 4 + j1;
+                unsigned cj = (y1 >> (j1 << 3)) & 0xffu;  // meaningless when j1 == 4
+                if (j1 == 4) {
+                    // a ninth digit (%.6g just above 1e-4), then the delimiter
+                    cj = reg[pf + 8];
+                    if (cj - '0' <= 9u) {
+                        frac = frac * 10u + (cj - '0');  // < 10^9
+                        nf = 9;
+                        cj = reg[pf + 9];
+                    }
+                }
+                if (ms_is_delim(cj)) {
+                    *bits_out = sign | ms_double_to_bits(ms_div_pow10_u32(frac, nf));
+                    *pp = pf + nf + 1;
+                    return cj != ',';
+                }
+            }
         } else {
-            // 1-3 digits and then the delimiter - unloaded force plates ("0"), sub-frames, CoP integers
             const uint32_t t = x ^ 0x30303030u;
             const uint32_t nd = ((t + 0x76767676u) | t) & 0x80808080u;
-            const int j = (__ffs(nd) - 1) >> 3;  // nd == 0 gives -1: no shortcut
-            if (j > 0) {
-                const unsigned cj = (x >> (j << 3)) & 0xffu;
-                if (ms_is_delim(cj)) {
-                    const uint32_t iv = ms_digits4(t << ((4 - j) << 3));
-                    *bits_out = sign | ms_double_to_bits((double)iv);
-                    *pp = p + j + 1;
-                    return cj != ',';
+            const int j0 = (__ffs(nd) - 1) >> 3;  // digits before the first other byte; nd == 0 gives -1
+            if (j0 > 0) {
+                const unsigned c0 = (x >> (j0 << 3)) & 0xffu;
+                const uint32_t ip = ms_digits4(t << ((4 - j0) << 3));  // the 1-3 leading digits
+                if (ms_is_delim(c0)) {
+                    // an integer - unloaded force plates ("0"), sub-frames, CoP values
+                    *bits_out = sign | ms_double_to_bits((double)ip);
+                    *pp = p + j0 + 1;
+                    return c0 != ',';
                 }
             }
         }
