@@ -343,7 +343,7 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     }
 }
 
-__global__ void __launch_bounds__(NMF_THREADS)
+__global__ void __launch_bounds__(NMF_THREADS, 3)
     ms_nmf_resident_kernel(const float* __restrict__ X, int n, int m, const MsNmfProblem* __restrict__ problems,
                            float* __restrict__ Wg, float* __restrict__ Hg, int max_iter, float tol, int check_every,
                            int32_t* __restrict__ n_iter_out, float* __restrict__ err_out, float* __restrict__ vaf_out) {
