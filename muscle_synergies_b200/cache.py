@@ -141,6 +141,7 @@ def _describe(data: ViconNexusData, source: Optional[str]) -> Tuple[dict, list]:
 
 def save_trial(data: ViconNexusData, path, source: Optional[dict] = None) -> None:
     """Writes the parsed trial to `path` (one device->host copy per section unless already made)."""
+    data.check()  # a trial loaded with defer_check=True must not be cached before its rows are known good
     head, section_blocks = _describe(data, source)
     write_trial_file(path, head, [b.host() for b in section_blocks])
 
