@@ -44,7 +44,10 @@ struct MsWorkspaceView {
     unsigned long long* term_prefix;  // terminator ends before the tile
     uint32_t* masks;                  // per 16-byte segment: terminator-end bits | comma bits << 16
     uint8_t* tile_in_quote;           // quote-aware rescan only: csv in-quote state at the start of each tile
+    uint2* brief;                     // per tile {n_term, flags | MS_TB_*}: what ms_resolve_kernel reads of most tiles
 };
+#define MS_TB_HAS_BLANK 0x100u   // the tile decided blank rows itself (blank_pos[] is not empty)
+#define MS_TB_HAS_QUOTES 0x200u  // n_quotes != 0
 
 __host__ __device__ static inline int64_t ms_align_up(int64_t x, int64_t a) { return (x + a - 1) / a * a; }
 
@@ -57,6 +60,8 @@ static MsWorkspaceView ms_view(void* ws, int64_t n_tiles, int64_t n_bytes_for_vi
     v.masks = (uint32_t*)p;
     p += ms_align_up((n_bytes_for_view + 15) / 16 * 4 + 32, 256);
     v.tile_in_quote = (uint8_t*)p;
+    p += ms_align_up(n_tiles, 256);
+    v.brief = (uint2*)p;
     return v;
 }
 
@@ -72,7 +77,7 @@ extern "C" int64_t ms_workspace_bytes(int64_t n_bytes) {
     int64_t t = ms_num_tiles(n_bytes < 1 ? 1 : n_bytes);
     int64_t nb = n_bytes < 1 ? 1 : n_bytes;
     return ms_align_up(t * (int64_t)sizeof(MsTileInfo), 256) + ms_align_up((t + 1) * 8, 256) +
-           ms_align_up((nb + 15) / 16 * 4 + 32, 256) + ms_align_up(t, 256);
+           ms_align_up((nb + 15) / 16 * 4 + 32, 256) + ms_align_up(t, 256) + ms_align_up(t * 8, 256);
 }
 
 // ---- shared helpers --------------------------------------------------------------------------------
@@ -134,7 +139,8 @@ template <int SCAN_WARPS, bool QUOTES>
 __global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t* __restrict__ src, int64_t n,
                                                                    MsTileInfo* __restrict__ tiles,
                                                                    uint32_t* __restrict__ masks,
-                                                                   const uint8_t* __restrict__ tile_in_quote) {
+                                                                   const uint8_t* __restrict__ tile_in_quote,
+                                                                   uint2* __restrict__ brief) {
     constexpr int SCAN_SPAN = MS_TILE_BYTES / SCAN_WARPS;  // bytes of the tile one warp walks
     constexpr int SCAN_ITERS = SCAN_SPAN / 512;
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -368,6 +374,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t*
         ti.pad[0] = ti.pad[1] = 0;
         ti.flags = f;
         tiles[tile] = ti;
+        brief[tile] = make_uint2(ti.n_term, f | (n_blank ? MS_TB_HAS_BLANK : 0u) | (ti.n_quotes ? MS_TB_HAS_QUOTES : 0u));
     }
 }
 
@@ -409,16 +416,16 @@ __device__ unsigned long long ms_block_count_terms(const uint32_t* __restrict__ 
 
 __global__ void __launch_bounds__(RESOLVE_THREADS)
     ms_resolve_kernel(const uint32_t* __restrict__ masks, int64_t n, const MsTileInfo* __restrict__ tiles,
-                      unsigned long long* __restrict__ term_prefix, int64_t n_tiles, ms_scan_summary* __restrict__ out) {
+                      const uint2* __restrict__ brief, unsigned long long* __restrict__ term_prefix, int64_t n_tiles,
+                      ms_scan_summary* __restrict__ out) {
     const int tid = threadIdx.x;
     __shared__ unsigned long long s_scan[RESOLVE_THREADS / 32];
-    __shared__ unsigned long long s_running, s_quotes, s_blank_total, s_acc;
+    __shared__ unsigned long long s_quotes, s_blank_total, s_acc;
     __shared__ uint32_t s_flags;
     __shared__ int s_ncand;
     __shared__ long long s_cand[RESOLVE_CAND_CAP];
 
     if (tid == 0) {
-        s_running = 0;
         s_quotes = 0;
         s_blank_total = 0;
         s_flags = 0;
@@ -426,59 +433,66 @@ __global__ void __launch_bounds__(RESOLVE_THREADS)
     }
     __syncthreads();
 
-    // ---- exclusive prefix of terminator counts
-    for (int64_t base = 0; base < n_tiles; base += RESOLVE_THREADS) {
-        int64_t k = base + tid;
-        unsigned long long v = k < n_tiles ? tiles[k].n_term : 0ull;
-        unsigned long long inc = v;
-        for (int o = 1; o < 32; o <<= 1) {
-            unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
-            if ((tid & 31) >= o) inc += t;
-        }
-        if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
-        __syncthreads();
-        unsigned long long wbase = 0;
-        for (int w = 0; w < (tid >> 5); w++) wbase += s_scan[w];
-        unsigned long long run = s_running;
-        if (k < n_tiles) term_prefix[k] = run + wbase + inc - v;
-        __syncthreads();
-        if (tid == RESOLVE_THREADS - 1) s_running = run + wbase + inc;
-        __syncthreads();
+    // Every thread owns a run of consecutive tiles and reads only their 8-byte briefs (coalesced across the
+    // block; the 64-byte records are touched for the rare tiles with blank rows or quotes): a thread sums
+    // its run's terminator counts, one block-wide scan turns the sums into bases, and a second sweep over
+    // the run writes the prefix and settles the rows that straddle tiles.
+    const int64_t per = (n_tiles + RESOLVE_THREADS - 1) / RESOLVE_THREADS;
+    const int64_t k0 = min(n_tiles, (int64_t)tid * per), k1 = min(n_tiles, k0 + per);
+    unsigned long long v = 0;
+    for (int64_t k = k0; k < k1; k++) v += brief[k].x;
+    unsigned long long inc = v;
+    for (int o = 1; o < 32; o <<= 1) {
+        unsigned long long t = __shfl_up_sync(0xffffffffu, inc, o);
+        if ((tid & 31) >= o) inc += t;
     }
-    if (tid == 0) term_prefix[n_tiles] = s_running;
+    if ((tid & 31) == 31) s_scan[tid >> 5] = inc;
+    __syncthreads();
+    unsigned long long run = inc - v;
+    for (int w = 0; w < (tid >> 5); w++) run += s_scan[w];
+    if (tid == RESOLVE_THREADS - 1) term_prefix[n_tiles] = run + v;
 
     // ---- blank rows
     unsigned long long my_quotes = 0, my_blank = 0;
     uint32_t my_flags = 0;
-    for (int64_t k = tid; k < n_tiles; k += RESOLVE_THREADS) {
-        MsTileInfo ti = tiles[k];
-        my_quotes += ti.n_quotes;
-        if (ti.flags & MS_TI_HIGH) my_flags |= MS_SCAN_HAS_HIGH_BYTES;
-        if (ti.flags & MS_TI_OVERFLOW) my_flags |= MS_SCAN_BLANK_OVERFLOW;
-        if (ti.flags & MS_TI_HAS_CR) my_flags |= MS_SCAN_HAS_CR;
+    uint32_t prev_flags = k0 > 0 ? brief[k0 - 1].y : 0u;  // flags of tile k - 1
+    for (int64_t k = k0; k < k1; k++) {
+        const uint2 bf = brief[k];
+        term_prefix[k] = run;
+        run += bf.x;
+        if (bf.y & MS_TI_HIGH) my_flags |= MS_SCAN_HAS_HIGH_BYTES;
+        if (bf.y & MS_TI_OVERFLOW) my_flags |= MS_SCAN_BLANK_OVERFLOW;
+        if (bf.y & MS_TI_HAS_CR) my_flags |= MS_SCAN_HAS_CR;
         const int64_t t0 = k * (int64_t)MS_TILE_BYTES;
-        my_blank += ti.n_blank;
-        for (int i = 0; i < MS_TILE_BLANK_SLOTS; i++) {
-            if (ti.blank_pos[i] >= 0) {
-                int slot = atomicAdd(&s_ncand, 1);
-                if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.blank_pos[i];
+        if (bf.y & (MS_TB_HAS_BLANK | MS_TB_HAS_QUOTES)) {
+            const MsTileInfo ti = tiles[k];
+            my_quotes += ti.n_quotes;
+            my_blank += ti.n_blank;
+            for (int i = 0; i < MS_TILE_BLANK_SLOTS; i++) {
+                if (ti.blank_pos[i] >= 0) {
+                    int slot = atomicAdd(&s_ncand, 1);
+                    if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.blank_pos[i];
+                }
             }
         }
-        if (ti.flags & MS_TI_HAS_TERM) {
+        if (bf.y & MS_TI_HAS_TERM) {
             // the row ending at this tile's first terminator began in an earlier tile (or at
             // the first byte of this one): walk back to the previous terminator
-            uint32_t acc = 0;
-            for (int64_t j = k - 1; j >= 0; j--) {
-                uint32_t f = tiles[j].flags;
-                acc |= f & MS_TI_NB_TAIL;
-                if (f & MS_TI_HAS_TERM) break;
+            uint32_t acc = prev_flags & MS_TI_NB_TAIL;
+            if (k > 0 && !(prev_flags & MS_TI_HAS_TERM)) {
+                for (int64_t j = k - 2; j >= 0; j--) {
+                    const uint32_t f = brief[j].y;
+                    acc |= f & MS_TI_NB_TAIL;
+                    if (f & MS_TI_HAS_TERM) break;
+                }
             }
-            if (!acc && !(ti.flags & MS_TI_NB_HEAD)) {
+            if (!acc && !(bf.y & MS_TI_NB_HEAD)) {
                 my_blank += 1;
                 int slot = atomicAdd(&s_ncand, 1);
-                if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + ti.first_term;
+                if (slot < RESOLVE_CAND_CAP) s_cand[slot] = t0 + tiles[k].first_term;
             }
         }
+        prev_flags = bf.y;
     }
     // tiles with more than MS_TILE_BLANK_SLOTS decided blank rows: the rest is not recorded;
     // harmless unless they are among the first MS_MAX_BLANK_ROWS of the file (flagged below)
@@ -1101,17 +1115,17 @@ static int ms_scan_impl(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspa
     if (n_tiles > 0) {
         if (!quoted) {
             ms_scan_kernel<SCAN_WARPS_MAX, false>
-                <<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, nullptr);
+                <<<(unsigned)n_tiles, SCAN_THREADS, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, nullptr, v.brief);
         } else {
             // in-quote state at every tile start from the quote counts of the plain scan
             ms_quote_parity_kernel<<<1, 1, 0, st>>>(v.tiles, n_tiles, v.tile_in_quote);
             MS_COUNT_LAUNCH();
-            ms_scan_kernel<1, true><<<(unsigned)n_tiles, 32, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, v.tile_in_quote);
+            ms_scan_kernel<1, true><<<(unsigned)n_tiles, 32, 0, st>>>(d_bytes, n_bytes, v.tiles, v.masks, v.tile_in_quote, v.brief);
         }
         MS_COUNT_LAUNCH();
         MS_CUDA_CHECK(cudaGetLastError());
     }
-    ms_resolve_kernel<<<1, RESOLVE_THREADS, 0, st>>>(v.masks, n_bytes, v.tiles, v.term_prefix, n_tiles, d_summary);
+    ms_resolve_kernel<<<1, RESOLVE_THREADS, 0, st>>>(v.masks, n_bytes, v.tiles, v.brief, v.term_prefix, n_tiles, d_summary);
     MS_COUNT_LAUNCH();
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
