@@ -18,6 +18,7 @@ replays the reference's rule on that single row to raise the same
 There is no CPU data path: without a CUDA device or without libms_b200.so every entry
 point raises.
 """
+import contextlib
 import ctypes
 import os
 import re
@@ -46,6 +47,7 @@ from .header import (
 _TERMINATOR = re.compile(rb"\r\n|\r|\n")
 _HEADER_LINES = 5
 _PEEK = 1 << 13  # bytes of header text fetched with the scan summary; take_lines' first window
+_META_INFO = 256  # offset of the peek's {offset, count} behind the scan summary in the loader's meta buffer
 _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 
@@ -135,10 +137,12 @@ class ViconLoader:
         self.stream = stream
         self.lib = nat.lib()
         self._pinned = None
-        self._pinned_summary = torch.empty(ctypes.sizeof(nat.ScanSummary) + 8, dtype=torch.uint8, pin_memory=True)
-        # header text that travels with the summary: [0, PEEK) of the file, then {offset, count} and the PEEK bytes
-        # after the first blank row (ms_peek_after_blank)
-        self._pinned_peek = torch.empty(2 * _PEEK + 16, dtype=torch.uint8, pin_memory=True)
+        # what every scan sends back: [summary | {offset, count} | the PEEK bytes after the first blank row]
+        # (ms_peek_after_blank) in one copy, and the first PEEK bytes of the file; buffers live with the loader
+        self._d_meta = torch.empty(_META_INFO + 16 + _PEEK, dtype=torch.uint8, device=self.device)
+        self._pinned_meta = torch.empty(_META_INFO + 16 + _PEEK, dtype=torch.uint8, pin_memory=True)
+        self._pinned_head = torch.empty(_PEEK, dtype=torch.uint8, pin_memory=True)
+        self._pinned_status = torch.empty(1, dtype=torch.int64, pin_memory=True)
 
     # ---- public -----------------------------------------------------------------------------
     def load_file(self, csv_filename) -> ViconNexusData:
@@ -211,36 +215,41 @@ class ViconLoader:
                 d_bytes[:n].copy_(staging[:n], non_blocking=True)
         return self._run(_Source(d_bytes, n, host), name)
 
+    def _on_stream(self, stream):
+        """Context that makes `stream` current - nothing to do when the loader uses the current stream."""
+        return self.torch.cuda.stream(stream) if self.stream is not None else contextlib.nullcontext()
+
     def _scan(self, src: _Source, ws=None):
         """ms_scan (or, when `ws` holds a previous scan, the quote-aware ms_scan_quoted)."""
         torch = self.torch
         stream, sptr = self._stream_ptr()
         ws_bytes = int(self.lib.ms_workspace_bytes(src.n))
         entry, what = (self.lib.ms_scan, "ms_scan") if ws is None else (self.lib.ms_scan_quoted, "ms_scan_quoted")
-        with torch.cuda.stream(stream):
+        # device side of what travels back: [summary | {offset, count} of the peek | peek bytes], one copy
+        meta = self._d_meta
+        d_summary, d_info, d_peek = meta.data_ptr(), meta.data_ptr() + _META_INFO, meta.data_ptr() + _META_INFO + 16
+        with self._on_stream(stream):
             if ws is None:
                 ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-            d_summary = torch.empty(ctypes.sizeof(nat.ScanSummary), dtype=torch.uint8, device=self.device)
-            nat.check(entry(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary.data_ptr(), sptr), what)
-            self._pinned_summary[: d_summary.numel()].copy_(d_summary, non_blocking=True)
+            nat.check(entry(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), ws_bytes, d_summary, sptr), what)
             peek = src.host is None and src.n > 0
             if peek:
                 # both sections' header lines come back with the summary (one wait instead of three)
                 k0 = min(src.n, _PEEK)
-                self._pinned_peek[:k0].copy_(src.d_bytes[:k0], non_blocking=True)
-                d_peek = torch.empty(_PEEK + 16, dtype=torch.uint8, device=self.device)
-                nat.check(self.lib.ms_peek_after_blank(src.d_bytes.data_ptr(), src.n, d_summary.data_ptr(), 0,
-                                                       d_peek.data_ptr() + 16, _PEEK, d_peek.data_ptr(), sptr),
-                          "ms_peek_after_blank")
-                self._pinned_peek[_PEEK:].copy_(d_peek, non_blocking=True)
+                self._pinned_head[:k0].copy_(src.d_bytes[:k0], non_blocking=True)
+                nat.check(self.lib.ms_peek_after_blank(src.d_bytes.data_ptr(), src.n, d_summary, 0, d_peek, _PEEK, d_info,
+                                                       sptr), "ms_peek_after_blank")
+                self._pinned_meta.copy_(meta, non_blocking=True)
+            else:
+                self._pinned_meta[:_META_INFO].copy_(meta[:_META_INFO], non_blocking=True)
         stream.synchronize()
-        summary = nat.ScanSummary.from_buffer_copy(self._pinned_summary.numpy()[: d_summary.numel()].tobytes())
+        host = self._pinned_meta.numpy()
+        summary = nat.ScanSummary.from_buffer_copy(host[: ctypes.sizeof(nat.ScanSummary)].tobytes())
         if peek:
-            host = self._pinned_peek.numpy()
-            src.windows = [(0, host[:k0].tobytes())]
-            off2, cnt2 = (int(v) for v in host[_PEEK : _PEEK + 16].view(np.int64))
+            src.windows = [(0, self._pinned_head.numpy()[:k0].tobytes())]
+            off2, cnt2 = (int(v) for v in host[_META_INFO : _META_INFO + 16].view(np.int64))
             if off2 >= 0 and cnt2 > 0:
-                src.windows.append((off2, host[_PEEK + 16 : _PEEK + 16 + cnt2].tobytes()))
+                src.windows.append((off2, host[_META_INFO + 16 : _META_INFO + 16 + cnt2].tobytes()))
         return summary, ws
 
     def _run(self, src: _Source, name: str, defer_check: bool = False) -> ViconNexusData:
@@ -257,7 +266,7 @@ class ViconLoader:
         sections = (nat.Section * nat.MS_MAX_SECTIONS)()
         blocks: List[Optional[SectionBlock]] = []
         n_sec = 0
-        with torch.cuda.stream(stream):
+        with self._on_stream(stream):
             for lay, (r0, r1) in zip(plan.layouts, plan.data_rows):
                 if lay is None or not lay.complete:
                     blocks.append(None)
@@ -280,7 +289,7 @@ class ViconLoader:
             if defer_check:
                 h_status = torch.empty(1, dtype=torch.int64, pin_memory=True)  # outlives this call
             else:
-                h_status = self._pinned_summary[-8:].view(torch.int64)
+                h_status = self._pinned_status
             h_status.copy_(d_status, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(stream)
