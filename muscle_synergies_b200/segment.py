@@ -16,6 +16,7 @@ alternations the reference silently re-appends a stale index (:745-752); this im
 raises ValueError instead.  Parity is claimed only when all transitions exist.
 """
 import ctypes
+import threading
 from collections import OrderedDict
 from enum import Enum, auto
 from typing import List, Mapping, Optional, Sequence, Tuple, Union
@@ -66,6 +67,25 @@ def _fz_tensor(dev: DeviceData):
     return dev.tensor[coords.index("Fz")]
 
 
+_pinned_pool = threading.local()  # per thread: numel -> a few pinned buffers, handed out round-robin
+
+
+def _pinned_like(t):
+    """A pinned host buffer shaped like `t`; its contents are read right after the copy, so a small ring
+    per thread is enough."""
+    import torch
+
+    n = int(t.numel())
+    if not hasattr(_pinned_pool, "rings"):
+        _pinned_pool.rings = {}
+    ring = _pinned_pool.rings.setdefault((n, t.dtype), [[], 0])
+    if len(ring[0]) < 4:
+        ring[0].append(torch.empty(n, dtype=t.dtype, pin_memory=True))
+        return ring[0][-1]
+    ring[1] = (ring[1] + 1) % len(ring[0])
+    return ring[0][ring[1]]
+
+
 class _TransitionSearch:
     """ms_find_transitions queued on the current stream; `finish()` waits and reads the result.
     `extra_words` int64 slots follow the results in the same buffer (`extra`), so that work queued
@@ -110,7 +130,11 @@ class _TransitionSearch:
         import torch
 
         want = self.want
-        host = self.res.cpu()
+        # into pinned memory: a pageable destination goes through the driver's staging buffer and costs
+        # a few tens of microseconds on the critical path of every trial
+        host = _pinned_like(self.res)
+        host.copy_(self.res, non_blocking=True)
+        self.stream.synchronize()
         tail = host[want : want + self.tail_words].view(torch.int32)
         k = int(tail[want].item())
         if self.num_segments > 0 and k < self.num_segments:
