@@ -167,6 +167,7 @@ __global__ void __launch_bounds__(SCAN_WARPS * 32) ms_scan_kernel(const uint8_t*
     const int64_t span0 = t0 + warp * SCAN_SPAN;
     uint4 vcur = make_uint4(0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu, 0x2c2c2c2cu);
     if (span0 < n) vcur = ms_load16(src, span0 + lane * 16, n, 0x2c2c2c2cu);
+#pragma unroll 4
     for (int it = 0; it < SCAN_ITERS; it++) {
         const int rel = warp * SCAN_SPAN + it * 512 + lane * 16;
         const int64_t off = t0 + rel;
