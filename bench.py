@@ -90,6 +90,26 @@ class ClockSampler:
         self._thread = None
 
     def _run(self):
+        # NVML in-process (a sample every 10 ms: the timed region of a short run is tens of milliseconds);
+        # nvidia-smi, one process per sample, only when the binding is missing
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            h = pynvml.nvmlDeviceGetHandleByIndex(self.gpu_index)
+            smax = pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM)
+            while not self._stop.is_set():
+                sm = pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)
+                try:
+                    why = pynvml.nvmlDeviceGetCurrentClocksEventReasons(h)
+                except Exception:  # noqa: BLE001 - older bindings
+                    why = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                flags = ["Active" if why & b else "Not Active" for b in (0x8, 0x40, 0x20, 0x4)]
+                self.samples.append(["", str(sm), str(smax), "", ""] + flags)
+                self._stop.wait(0.01)
+            return
+        except Exception:  # noqa: BLE001
+            pass
         while not self._stop.is_set():
             try:
                 out = subprocess.run(
@@ -477,7 +497,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=int(os.environ.get("WORLD_SIZE", "1")))
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=50)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="T10", help="synthetic layout (tools/synth_vicon.py LAYOUTS)")
