@@ -39,7 +39,9 @@ extern "C" {
 #define MS_E_WORKSPACE (-3) /* workspace too small */
 #define MS_E_NO_DEVICE (-4) /* no CUDA device / wrong architecture */
 
+#ifndef MS_TILE_BYTES
 #define MS_TILE_BYTES 49152     /* bytes of CSV owned by one thread block */
+#endif
 #define MS_MAX_ROW_BYTES 8192   /* longest supported CSV row (overhang read past a tile) */
 #define MS_MAX_BLANK_ROWS 8     /* blank rows reported by ms_scan (first ones, file order) */
 #define MS_MAX_SECTIONS 4

@@ -847,7 +847,10 @@ __device__ __forceinline__ bool ms_parse_next(const uint8_t* __restrict__ reg, i
 }
 
 
-__global__ void __launch_bounds__(PARSE_THREADS, 3)
+#ifndef PARSE_MIN_CTAS
+#define PARSE_MIN_CTAS 3
+#endif
+__global__ void __launch_bounds__(PARSE_THREADS, PARSE_MIN_CTAS)
     ms_parse_kernel(const uint8_t* __restrict__ src, int64_t n, const unsigned long long* __restrict__ term_prefix,
                     const uint32_t* __restrict__ masks, const MsSectionsArg secs,
                     unsigned long long* __restrict__ status) {
