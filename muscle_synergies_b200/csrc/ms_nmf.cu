@@ -467,77 +467,196 @@ struct MsNmfStreamState {  // per problem, device memory
     int n_iter, done;
 };
 
+// One pass over X and W for one problem: per 256-row tile, stage X and W (float4 rows, same padded layout
+// as the resident kernel), update the W rows (one row per thread, H^T and H H^T as broadcast float4), write them
+// back, and accumulate W^T W / W^T X in a 4 x 4 register tile that lives across all the tiles a CTA visits -
+// shared memory is read as float4 only, and the reduction happens once, at the end, with global atomics.
+// The tiles are double-buffered: the 16-byte asynchronous copies (cp.async) of the next tile are in flight while
+// this one is computed, so the pass runs at memory speed instead of waiting out a round trip per tile.
+__device__ __forceinline__ void ms_cp_async16(void* smem_dst, const void* gmem_src) {
+    const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;\n" ::"r"(d), "l"(gmem_src) : "memory");
+}
+
 template <int K>
 __device__ __forceinline__ void ms_nmf_stream_w_body(const float* __restrict__ X, long long n, int m, float* __restrict__ Wp,
                                                      const float* __restrict__ Hp, MsNmfStreamState* __restrict__ stt,
                                                      float* sm) {
-    const int xs = m | 1;
-    constexpr int ws = K | 1;
-    float* sX = sm;                    // [NMFS_ROWS][xs]
-    float* sW = sX + NMFS_ROWS * xs;   // [NMFS_ROWS][ws]
-    float* sH = sW + NMFS_ROWS * ws;   // [K][m]
-    float* sHHt = sH + K * m;          // [K][K]
+    constexpr int KP = (K + 3) & ~3, KQ = KP / 4;
+    constexpr int WS = ((KP >> 2) & 1) ? KP : KP + 4;
+    const int MP = ms_nmf_pad4(m), MQ = MP / 4, XS = ms_nmf_stride(MP);
+    float* sXb = sm;                          // [2][NMFS_ROWS][XS]
+    float* sWb = sXb + 2 * NMFS_ROWS * XS;    // [2][NMFS_ROWS][WS]
+    float* sHt = sWb + 2 * NMFS_ROWS * WS;    // [MP][KP]
+    float* sHHt = sHt + MP * KP;              // [K][KP]
     const int tid = threadIdx.x;
-    for (int i = tid; i < K * m; i += NMFS_ROWS) sH[i] = Hp[i];
-    for (int i = tid; i < K * K; i += NMFS_ROWS) sHHt[i] = stt->HHt[i];
-    const int pairs = K * K + K * m;
-    int split = NMFS_ROWS / pairs;
-    if (split < 1) split = 1;
-    const int rows_per = (NMFS_ROWS + split - 1) / split;
-    float accum[(NMF_MAX_K * NMF_MAX_K + NMF_MAX_K * NMF_MAX_M + NMFS_ROWS - 1) / NMFS_ROWS];
+    for (int i = tid; i < 2 * NMFS_ROWS * XS; i += NMFS_ROWS) sXb[i] = 0.f;  // the padding columns stay zero
+    for (int i = tid; i < 2 * NMFS_ROWS * WS; i += NMFS_ROWS) sWb[i] = 0.f;
+    for (int i = tid; i < MP * KP; i += NMFS_ROWS) {
+        const int j = i / KP, c = i - j * KP;
+        sHt[i] = (c < K && j < m) ? Hp[c * m + j] : 0.f;
+    }
+    for (int i = tid; i < K * KP; i += NMFS_ROWS) {
+        const int bq = i / KP, c = i - bq * KP;
+        sHHt[i] = c < K ? stt->HHt[bq * K + c] : 0.f;
+    }
+    // this thread's 4 x 4 tile of W^T W or W^T X and its slice of the rows of every tile
+    // (at most 4 * 4 + 4 * 16 = 80 tiles for k <= 16, m <= 64: one per thread is enough)
+    const int n_tiles4 = KQ * KQ + KQ * MQ;
+    const int slices = NMFS_ROWS / n_tiles4;
+    const int rows_per = (NMFS_ROWS + slices - 1) / slices;
+    const bool t2_active = tid < n_tiles4 * slices;
+    const int t4 = tid % n_tiles4, t2_i0 = (tid / n_tiles4) * rows_per;
+    int t2_left = 0, t2_right = 0, t2_rstride = WS;  // offsets inside the W / X buffers
+    bool t2_x = false;
+    if (t4 < KQ * KQ) {
+        t2_left = 4 * (t4 / KQ);
+        t2_right = 4 * (t4 % KQ);
+    } else {
+        const int q = t4 - KQ * KQ;
+        t2_left = 4 * (q / MQ);
+        t2_right = 4 * (q % MQ);
+        t2_rstride = XS;
+        t2_x = true;
+    }
+    float acc[4][4];
 #pragma unroll
-    for (int q = 0; q < (int)(sizeof(accum) / sizeof(float)); q++) accum[q] = 0.f;
+    for (int r = 0; r < 4; r++)
+#pragma unroll
+        for (int c = 0; c < 4; c++) acc[r][c] = 0.f;
+    // float4 global accesses need 16-byte aligned rows: whole float4 groups per row and an aligned base (a
+    // problem's W starts wherever the previous problems' factors end)
+    const bool vec_x = (m & 3) == 0 && (reinterpret_cast<uintptr_t>(X) & 15) == 0;
+    const bool vec_w = (K & 3) == 0 && (reinterpret_cast<uintptr_t>(Wp) & 15) == 0;
     const long long n_tiles = (n + NMFS_ROWS - 1) / NMFS_ROWS;
-    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+
+    auto prefetch = [&](long long tile, int buf) {  // the aligned parts of a tile, asynchronously
+        if (tile < n_tiles) {
+            const long long r0 = tile * NMFS_ROWS;
+            const int rows = (int)min((long long)NMFS_ROWS, n - r0);
+            if (vec_x) {
+                const float* src = X + r0 * m;
+                float* dst = sXb + buf * NMFS_ROWS * XS;
+                for (int i = tid; i < rows * MQ; i += NMFS_ROWS) {
+                    const int r = i / MQ, q = i - r * MQ;
+                    ms_cp_async16(dst + r * XS + 4 * q, src + 4 * i);
+                }
+            }
+            if (vec_w) {
+                const float* src = Wp + r0 * K;
+                float* dst = sWb + buf * NMFS_ROWS * WS;
+                for (int i = tid; i < rows * KQ; i += NMFS_ROWS) {
+                    const int r = i / KQ, q = i - r * KQ;
+                    ms_cp_async16(dst + r * WS + 4 * q, src + 4 * i);
+                }
+            }
+        }
+        asm volatile("cp.async.commit_group;\n" ::: "memory");
+    };
+
+    __syncthreads();  // the zero fill above must not race with the first copies
+    int buf = 0;
+    prefetch(blockIdx.x, 0);
+    for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, buf ^= 1) {
         const long long r0 = tile * NMFS_ROWS;
         const int rows = (int)min((long long)NMFS_ROWS, n - r0);
-        __syncthreads();
-        for (int i = tid; i < rows * m; i += NMFS_ROWS) sX[(i / m) * xs + (i % m)] = X[r0 * m + i];
-        for (int i = tid; i < rows * K; i += NMFS_ROWS) sW[(i / K) * ws + (i % K)] = Wp[r0 * K + i];
+        float* sX = sXb + buf * NMFS_ROWS * XS;
+        float* sW = sWb + buf * NMFS_ROWS * WS;
+        prefetch(tile + gridDim.x, buf ^ 1);  // nobody reads that buffer any more: see the barrier at the loop's end
+        if (!vec_x)
+            for (int i = tid; i < rows * m; i += NMFS_ROWS) sX[(i / m) * XS + (i % m)] = X[r0 * m + i];
+        if (!vec_w)
+            for (int i = tid; i < rows * K; i += NMFS_ROWS) sW[(i / K) * WS + (i % K)] = Wp[r0 * K + i];
+        asm volatile("cp.async.wait_group 1;\n" ::: "memory");  // this tile's copies (the next tile's may still fly)
         __syncthreads();
         if (tid < rows) {
-            float w[K], num[K];
+            const int i = tid;
+            float w[KP], num[KP], den[KP];
 #pragma unroll
-            for (int c = 0; c < K; c++) {
-                w[c] = sW[tid * ws + c];
-                num[c] = 0.f;
-            }
-            for (int j = 0; j < m; j++) {
-                const float x = sX[tid * xs + j];
-#pragma unroll
-                for (int c = 0; c < K; c++) num[c] = fmaf(x, sH[c * m + j], num[c]);
+            for (int q = 0; q < KQ; q++) {
+                const float4 v = *reinterpret_cast<const float4*>(sW + i * WS + 4 * q);
+                w[4 * q] = v.x, w[4 * q + 1] = v.y, w[4 * q + 2] = v.z, w[4 * q + 3] = v.w;
             }
 #pragma unroll
-            for (int c = 0; c < K; c++) {
-                float den = 0.f;
+            for (int c = 0; c < KP; c++) num[c] = den[c] = 0.f;
+            for (int jq = 0; jq < MQ; jq++) {
+                const float4 xv = *reinterpret_cast<const float4*>(sX + i * XS + 4 * jq);
+                const float x4[4] = {xv.x, xv.y, xv.z, xv.w};
 #pragma unroll
-                for (int b = 0; b < K; b++) den = fmaf(w[b], sHHt[b * K + c], den);
-                if (den == 0.f) den = NMF_EPS;
-                sW[tid * ws + c] = w[c] * (num[c] / den);
+                for (int jj = 0; jj < 4; jj++) {
+                    const float* ht = sHt + (4 * jq + jj) * KP;
+#pragma unroll
+                    for (int q = 0; q < KQ; q++) {
+                        const float4 h = *reinterpret_cast<const float4*>(ht + 4 * q);
+                        num[4 * q] = fmaf(x4[jj], h.x, num[4 * q]);
+                        num[4 * q + 1] = fmaf(x4[jj], h.y, num[4 * q + 1]);
+                        num[4 * q + 2] = fmaf(x4[jj], h.z, num[4 * q + 2]);
+                        num[4 * q + 3] = fmaf(x4[jj], h.w, num[4 * q + 3]);
+                    }
+                }
             }
+#pragma unroll
+            for (int bq = 0; bq < K; bq++) {
+#pragma unroll
+                for (int q = 0; q < KQ; q++) {
+                    const float4 g = *reinterpret_cast<const float4*>(sHHt + bq * KP + 4 * q);
+                    den[4 * q] = fmaf(w[bq], g.x, den[4 * q]);
+                    den[4 * q + 1] = fmaf(w[bq], g.y, den[4 * q + 1]);
+                    den[4 * q + 2] = fmaf(w[bq], g.z, den[4 * q + 2]);
+                    den[4 * q + 3] = fmaf(w[bq], g.w, den[4 * q + 3]);
+                }
+            }
+#pragma unroll
+            for (int c = 0; c < KP; c++) {
+                const float d = den[c] == 0.f ? NMF_EPS : den[c];
+                w[c] = w[c] * (num[c] / d);  // padding components: 0 * (0 / eps) = 0
+            }
+#pragma unroll
+            for (int q = 0; q < KQ; q++)
+                *reinterpret_cast<float4*>(sW + i * WS + 4 * q) = make_float4(w[4 * q], w[4 * q + 1], w[4 * q + 2], w[4 * q + 3]);
         }
         __syncthreads();
-        for (int i = tid; i < rows * K; i += NMFS_ROWS) Wp[r0 * K + i] = sW[(i / K) * ws + (i % K)];
-        int q = 0;
-        for (int e = tid; e < pairs * split; e += NMFS_ROWS, q++) {
-            const int pair = e % pairs, sl = e / pairs;
-            const int i0 = sl * rows_per, i1 = min(rows, i0 + rows_per);
-            float acc = 0.f;
-            if (pair < K * K) {
-                const int a = pair / K, b = pair % K;
-                for (int i = i0; i < i1; i++) acc = fmaf(sW[i * ws + a], sW[i * ws + b], acc);
-            } else {
-                const int qq = pair - K * K, a = qq / m, j = qq % m;
-                for (int i = i0; i < i1; i++) acc = fmaf(sW[i * ws + a], sX[i * xs + j], acc);
+        if (vec_w) {
+            float4* dst = reinterpret_cast<float4*>(Wp + r0 * K);
+            for (int i = tid; i < rows * KQ; i += NMFS_ROWS) {
+                const int r = i / KQ, q = i - r * KQ;
+                dst[i] = *reinterpret_cast<const float4*>(sW + r * WS + 4 * q);
             }
-            accum[q] += acc;
+        } else {
+            for (int i = tid; i < rows * K; i += NMFS_ROWS) Wp[r0 * K + i] = sW[(i / K) * WS + (i % K)];
         }
+        if (t2_active) {
+            const float* left = sW + t2_left;
+            const float* right = (t2_x ? sX : sW) + t2_right;
+            const int i1 = min(rows, t2_i0 + rows_per);
+#pragma unroll 2
+            for (int i = t2_i0; i < i1; i++) {
+                const float4 av = *reinterpret_cast<const float4*>(left + i * WS);
+                const float4 bv = *reinterpret_cast<const float4*>(right + i * t2_rstride);
+                const float a4[4] = {av.x, av.y, av.z, av.w}, b4[4] = {bv.x, bv.y, bv.z, bv.w};
+#pragma unroll
+                for (int r = 0; r < 4; r++)
+#pragma unroll
+                    for (int c = 0; c < 4; c++) acc[r][c] = fmaf(a4[r], b4[c], acc[r][c]);
+            }
+        }
+        __syncthreads();  // everyone is done with this buffer before the next iteration's copies land in it
     }
-    int q = 0;
-    for (int e = tid; e < pairs * split; e += NMFS_ROWS, q++) atomicAdd(&stt->acc[e % pairs], accum[q]);
+    asm volatile("cp.async.wait_group 0;\n" ::: "memory");
+    // one reduction per CTA: tile element (r, c) -> W^T W [K][K], then W^T X [K][m] behind it
+    if (t2_active) {
+#pragma unroll
+        for (int r = 0; r < 4; r++)
+#pragma unroll
+            for (int c = 0; c < 4; c++) {
+                const int a = t2_left + r, bcol = t2_right + c;
+                const int width = t2_x ? m : K, base = t2_x ? K * K : 0;
+                if (a < K && bcol < width) atomicAdd(&stt->acc[base + a * width + bcol], acc[r][c]);
+            }
+    }
 }
 
-__global__ void __launch_bounds__(NMFS_ROWS)
+__global__ void __launch_bounds__(NMFS_ROWS, 3)
     ms_nmf_stream_w_kernel(const float* __restrict__ X, long long n, int m, const MsNmfProblem* __restrict__ problems,
                            float* __restrict__ Wg, const float* __restrict__ Hg, MsNmfStreamState* __restrict__ states) {
     extern __shared__ float sm[];
@@ -730,11 +849,12 @@ extern "C" int ms_nmf_mu_stream(const float* d_X, int64_t n, int32_t m, const in
     MS_CUDA_CHECK(e);
 
     const long long n_tiles = (n + NMFS_ROWS - 1) / NMFS_ROWS;
-    int ctas = (148 * 4 + n_problems - 1) / n_problems;
+    int ctas = (148 * 3 + n_problems - 1) / n_problems;  // three CTAs of the W pass fit an SM: one wave
     if (ctas > n_tiles) ctas = (int)n_tiles;
     if (ctas < 1) ctas = 1;
-    const size_t smem = sizeof(float) * ((size_t)NMFS_ROWS * (m | 1) + (size_t)NMFS_ROWS * (kmax | 1) + (size_t)kmax * m +
-                                         (size_t)kmax * kmax);
+    const int KPmax = ms_nmf_pad4(kmax), MPs = ms_nmf_pad4(m);
+    const size_t smem = sizeof(float) * (2 * (size_t)NMFS_ROWS * ms_nmf_stride(MPs) + 2 * (size_t)NMFS_ROWS * ms_nmf_stride(KPmax) +
+                                         (size_t)MPs * KPmax + (size_t)kmax * KPmax);  // two tile buffers
     MS_CUDA_CHECK(cudaFuncSetAttribute(ms_nmf_stream_w_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     long long vaf_want = 148 * 8 / (n_problems < 8 ? n_problems : 8) + 1, vaf_cap = (long long)((n + 15) / 16);
     int vaf_ctas = (int)(vaf_want < vaf_cap ? vaf_want : vaf_cap);

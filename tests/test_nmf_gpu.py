@@ -175,6 +175,22 @@ def test_streaming_regime_matches_sklearn_and_the_resident_kernel(analysis, n, k
         assert np.abs(same.vaf - res.vaf).max() <= 2e-5
 
 
+def test_streaming_regime_with_unaligned_factor_offsets(analysis):
+    """A problem whose W starts at an odd float offset (after a rank-3 problem on 4999 rows) must take the
+    scalar global-memory path of the streaming kernel, the aligned ones the float4 path - same answers."""
+    from oracle import nmf_oracle as no
+
+    X = envelopes(6, n=4999)
+    ranks, seeds = [3, 4, 8, 4], [0, 1, 2, 3]
+    res = analysis.nmf_mu_batched(X, ranks, seeds, max_iter=30, tol=0.0, regime="stream")
+    for p, (kk, seed) in enumerate(zip(ranks, seeds)):
+        W, H, model = sklearn_run(X, kk, seed, 30, 0.0)
+        want_all, want_cols = no.vaf(X, W, H)
+        assert abs(res.vaf[p, 0] - want_all) <= VAF_TOL
+        assert np.abs(res.vaf[p, 1:] - want_cols).max() <= 2 * VAF_TOL
+        assert abs(res.err[p] - model.reconstruction_err_) / np.linalg.norm(X) <= ERR_TOL
+
+
 def test_streaming_regime_convergence_stop(analysis):
     X = envelopes(6, n=3000)
     res = analysis.nmf_mu_batched(X, [3], [2], max_iter=4000, tol=1e-5, regime="stream")
