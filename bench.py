@@ -258,6 +258,45 @@ def bench_pipeline(loader, d_bytes, n, layout, trials=3):
             "nmf_problems_per_trial": int(len(res.restarts)), "timing": "wall clock; factors, errors and VAF of every restart on the host (DataFrames are built on access)"}
 
 
+def bench_files(loader, blob, layout, copies=6):
+    """SURVEY.md section 8d, third number: files -> host arrays through `ViconLoader.load_files` (reader thread ->
+    pinned ring -> H2D / parse / D2H pipeline).  `copies` files of the trial in shared memory (or the temp
+    directory), page cache warm, wall clock."""
+    import shutil
+    import tempfile
+
+    import torch
+
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (copies + 1) * blob.nbytes else None
+    tmp = tempfile.mkdtemp(prefix="ms_b200_bench_", dir=base)
+    try:
+        paths = []
+        for i in range(copies):
+            path = os.path.join(tmp, f"trial{i}.csv")
+            with open(path, "wb") as f:
+                f.write(memoryview(blob))
+            paths.append(path)
+
+        def run():
+            last = None
+            for _name, data in loader.load_files(paths, to_host=True):
+                if isinstance(data, Exception):
+                    raise data
+                last = data
+            for blk in last.blocks:
+                blk.host()
+            torch.cuda.synchronize()
+
+        run()
+        t = time.perf_counter()
+        run()
+        wall = time.perf_counter() - t
+        return {"value": copies * blob.nbytes / wall / 1e9, "unit": UNIT, "files": copies, "ms_per_file": wall / copies * 1e3,
+                "where": "tmpfs" if base else "temp directory", "api": "ViconLoader.load_files -> host arrays, wall clock"}
+    finally:
+        shutil.rmtree(tmp, ignore_errors=True)
+
+
 # ---- reference arm ----------------------------------------------------------------------------------------
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
@@ -458,6 +497,13 @@ def run_ours(args):
         except Exception as exc:  # noqa: BLE001
             pipeline = {"error": f"{type(exc).__name__}: {exc}"}
 
+    from_files = None
+    if rank == 0 and world == 1:
+        try:
+            from_files = bench_files(loader, blob, layout)
+        except Exception as exc:  # noqa: BLE001
+            from_files = {"error": f"{type(exc).__name__}: {exc}"}
+
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, all_cpus)
@@ -485,6 +531,7 @@ def run_ours(args):
             "kernels_ms": {"ms_parse": t_parse, "ms_scan+resolve": t_scan},
             "nmf": nmf,
             "pipeline": pipeline,
+            "from_files": from_files,
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }

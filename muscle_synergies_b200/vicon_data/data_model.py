@@ -349,7 +349,9 @@ class DeviceData:
     @property
     def df(self) -> pd.DataFrame:
         if self._df is None:
-            self._df = pd.DataFrame(self.values_cm.T, columns=self._coords, dtype=float)
+            # zero-copy: the transposed rows of the channel-major host block ARE the (n_cols, n_rows) C-order
+            # block pandas stores; pandas 3 would otherwise copy every device's slice
+            self._df = pd.DataFrame(self.values_cm.T, columns=self._coords, dtype=float, copy=False)
         return self._df
 
     @df.setter

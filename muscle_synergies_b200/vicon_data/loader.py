@@ -51,6 +51,40 @@ _META_INFO = 256  # offset of the peek's {offset, count} behind the scan summary
 _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 
+_READ_CHUNK = 32 << 20
+_read_pool = None
+
+
+def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callable[[int, int], None]] = None) -> None:
+    """Reads the first `size` bytes of file `name` into the uint8 array `view` with several threads (one
+    thread copies out of the page cache at ~5 GB/s, a tenth of what the PCIe link then moves); `on_chunk(offset,
+    length)` is called in file order as the chunks complete."""
+    global _read_pool
+    if _read_pool is None:
+        from concurrent.futures import ThreadPoolExecutor
+
+        _read_pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) - 1)), thread_name_prefix="ms-read")
+    fd = os.open(name, os.O_RDONLY)
+    try:
+        mem = memoryview(view)
+
+        def part(off):
+            want = min(_READ_CHUNK, size - off)
+            got = 0
+            while got < want:
+                k = os.preadv(fd, [mem[off + got : off + want]], off + got)
+                if k <= 0:
+                    raise IOError(f"short read on {name}: {off + got} of {size} bytes")
+                got += k
+            return off, want
+
+        for off, want in _read_pool.map(part, range(0, size, _READ_CHUNK)):
+            if on_chunk is not None:
+                on_chunk(off, want)
+    finally:
+        os.close(fd)
+
+
 def _torch():
     import torch
 
@@ -150,11 +184,15 @@ class ViconLoader:
         size = os.path.getsize(csv_filename)  # FileNotFoundError propagates unwrapped, like open()
         staging = self._staging(size)
         view = staging.numpy()
-        with open(csv_filename, "rb") as fh:
-            got = fh.readinto(memoryview(view)[:size])
-        if got != size:
-            raise IOError(f"short read on {csv_filename}: {got} of {size} bytes")
-        return self._load_host(view[:size], staging, str(csv_filename))
+        stream, _ = self._stream_ptr()
+        with self._on_stream(stream):
+            d_bytes = torch.empty(_pad16(size), dtype=torch.uint8, device=self.device)
+
+            def uploaded(off, length):  # each chunk goes to the GPU while the next ones are still being read
+                d_bytes[off : off + length].copy_(staging[off : off + length], non_blocking=True)
+
+            read_file_into(csv_filename, view, size, uploaded)
+        return self._run(_Source(d_bytes, size, view[:size]), str(csv_filename))
 
     def load_bytes(self, data, name: str = "<bytes>") -> ViconNexusData:
         """`data`: bytes / bytearray / uint8 numpy array / uint8 CPU tensor holding the CSV."""
@@ -421,10 +459,7 @@ class ViconLoader:
                     if buf is None or buf.numel() < _pad16(size):
                         buf = torch.empty(max(_pad16(size), 1 << 20), dtype=torch.uint8, pin_memory=True)
                         ring[slot] = buf
-                    with open(name, "rb") as fh:
-                        got = fh.readinto(memoryview(buf.numpy())[:size])
-                    if got != size:
-                        raise IOError(f"short read on {name}: {got} of {size} bytes")
+                    read_file_into(name, buf.numpy(), size)
                     q.put((name, buf[:size]))
                 except Exception as exc:  # noqa: BLE001 - reported with the file it belongs to
                     q.put((name, exc))
