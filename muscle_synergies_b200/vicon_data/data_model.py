@@ -56,10 +56,12 @@ class SectionBlock:
             else:
                 import torch
 
+                # lazily, into ordinary memory: page-locking a fresh buffer of this size costs several times the
+                # copy itself; the pipelined loaders (load_many) bring their own pinned ring instead
                 view = self.tensor[:, : self.n_rows]
-                pinned = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
-                pinned.copy_(view, non_blocking=False)
-                self._host = pinned.numpy()
+                host = np.empty(tuple(view.shape), dtype=np.float64)
+                torch.from_numpy(host).copy_(view)
+                self._host = host
         return self._host
 
 
