@@ -65,10 +65,16 @@ __global__ void __launch_bounds__(CHASE_THREADS)
         while (base < n_words) {
             if (tid == 0) s_min = 0x7fffffffffffffffll;
             __syncthreads();
-            const int64_t w = base + tid;
-            uint32_t word = w < n_words ? bm[w] : 0u;
-            if (w == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
-            if (word) atomicMin(&s_min, (long long)(w * 32 + __ffs(word) - 1));
+            // two words per thread and round (independent loads): 65536 samples per round, so that a search
+            // across one gait phase usually ends in its first round - the rounds are what this kernel costs
+            const int64_t wa = base + tid, wb = wa + CHASE_THREADS;
+            uint32_t word_a = wa < n_words ? bm[wa] : 0u;
+            const uint32_t word_b = wb < n_words ? bm[wb] : 0u;
+            if (wa == (cursor >> 5)) word_a &= ~((1u << (cursor & 31)) - 1u);
+            if (word_a)
+                atomicMin(&s_min, (long long)(wa * 32 + __ffs(word_a) - 1));
+            else if (word_b)
+                atomicMin(&s_min, (long long)(wb * 32 + __ffs(word_b) - 1));
             __syncthreads();
             const long long m = s_min;
             __syncthreads();
@@ -76,7 +82,7 @@ __global__ void __launch_bounds__(CHASE_THREADS)
                 hit = m;
                 break;
             }
-            base += CHASE_THREADS;
+            base += 2 * CHASE_THREADS;
         }
         if (hit < 0) break;
         cursor = hit;
