@@ -13,11 +13,16 @@ spec = importlib.util.spec_from_file_location("tl", os.path.join(ROOT, "tests", 
 tl = importlib.util.module_from_spec(spec); spec.loader.exec_module(tl)
 
 first, count = int(sys.argv[1]), int(sys.argv[2])
+inject = len(sys.argv) > 3 and sys.argv[3] == "--bad"  # also plant fields float() rejects (error parity)
+
 bad = 0
+raised = 0
 with tempfile.TemporaryDirectory() as d:
     for seed in range(first, first + count):
         rnd = random.Random(seed)
-        blob = tl._ragged_file(rnd, rnd.randrange(1, 600), rnd.randrange(1, 80), rnd.choice(["\n", "\r\n", "\r"]))
+        blob = tl._ragged_file(rnd, rnd.randrange(1, 600), rnd.randrange(1, 80), "\n" if inject else rnd.choice(["\n", "\r\n", "\r"]))
+        if inject and rnd.random() < 0.8:
+            blob = tl._plant_bad_fields(blob, rnd)
         path = os.path.join(d, "f.csv")
         open(path, "wb").write(blob)
         try:
@@ -33,6 +38,7 @@ with tempfile.TemporaryDirectory() as d:
             print("seed", seed, "exception mismatch:", repr(werr), "vs", repr(gerr))
             continue
         if werr is not None:
+            raised += 1
             continue
         for dev, odev in zip(tl.all_devices(got), want.all_devices()):
             a, b = tl.bits(dev.df.to_numpy()), tl.bits(vo.device_array(odev))
@@ -40,4 +46,4 @@ with tempfile.TemporaryDirectory() as d:
                 bad += 1
                 print("seed", seed, "array mismatch in", dev.name)
                 break
-print("fuzzed", count, "files, mismatches:", bad)
+print("fuzzed", count, "files,", raised, "of them raise in the oracle; mismatches:", bad)
