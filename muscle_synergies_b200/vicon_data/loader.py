@@ -177,6 +177,7 @@ class ViconLoader:
         self._pinned_meta = torch.empty(_META_INFO + 16 + _PEEK, dtype=torch.uint8, pin_memory=True)
         self._pinned_head = torch.empty(_PEEK, dtype=torch.uint8, pin_memory=True)
         self._pinned_status = torch.empty(1, dtype=torch.int64, pin_memory=True)
+        self._side_streams = None  # copy-in / copy-out streams of load_many, created on first use
 
     # ---- public -----------------------------------------------------------------------------
     def load_file(self, csv_filename) -> ViconNexusData:
@@ -371,8 +372,11 @@ class ViconLoader:
         src_iter = iter(sources)
         name_iter = iter(names) if names is not None else None
         s_comp, _ = self._stream_ptr()
-        s_copy = torch.cuda.Stream(self.device)
-        s_d2h = torch.cuda.Stream(self.device)
+        # the side streams live with the loader: the caching allocator keeps a pool per stream, so fresh
+        # streams on every call would strand the previous call's blocks
+        if self._side_streams is None:
+            self._side_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        s_copy, s_d2h = self._side_streams
         ring = [dict() for _ in range(max(1, host_slots))]
         counter = [0]
 
