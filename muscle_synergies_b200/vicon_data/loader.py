@@ -454,8 +454,21 @@ class ViconLoader:
         ring = [None] * (read_ahead + 3)
         q = queue.Queue(maxsize=read_ahead)
 
+        stop = threading.Event()  # set when the consumer goes away before the last file
+
+        def hand_over(item) -> bool:
+            while not stop.is_set():
+                try:
+                    q.put(item, timeout=0.2)
+                    return True
+                except queue.Full:
+                    continue
+            return False
+
         def reader():
             for i, name in enumerate(names):
+                if stop.is_set():
+                    return
                 try:
                     size = os.path.getsize(name)
                     slot = i % len(ring)
@@ -464,12 +477,14 @@ class ViconLoader:
                         buf = torch.empty(max(_pad16(size), 1 << 20), dtype=torch.uint8, pin_memory=True)
                         ring[slot] = buf
                     read_file_into(name, buf.numpy(), size)
-                    q.put((name, buf[:size]))
+                    item = (name, buf[:size])
                 except Exception as exc:  # noqa: BLE001 - reported with the file it belongs to
-                    q.put((name, exc))
-            q.put(None)
+                    item = (name, exc)
+                if not hand_over(item):
+                    return
+            hand_over(None)
 
-        threading.Thread(target=reader, daemon=True).start()
+        threading.Thread(target=reader, daemon=True, name="ms-load-files").start()
 
         def sources():
             while True:
@@ -486,10 +501,13 @@ class ViconLoader:
                 yield src
 
         k = 0
-        for result in self.load_many(feed(), names=_LazyNames(order), to_host=to_host, host_slots=host_slots,
-                                     return_exceptions=True):
-            yield order[k], result
-            k += 1
+        try:
+            for result in self.load_many(feed(), names=_LazyNames(order), to_host=to_host, host_slots=host_slots,
+                                         return_exceptions=True):
+                yield order[k], result
+                k += 1
+        finally:
+            stop.set()  # a consumer that stops early must not leave the reader blocked on a full queue
 
 
 class _LazyNames:
