@@ -202,6 +202,7 @@ int ms_nmf_mu_stream(const float* d_X, int64_t n, int32_t m, const int32_t* h_ra
                      void* d_work, int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------- */
+/* Text of the last CUDA failure reported (MS_E_CUDA) to the calling thread. */
 const char* ms_last_cuda_error(void);
 const char* ms_version(void);
 /* Number of kernels this library has launched in this process (bench.py gpu_launches). */

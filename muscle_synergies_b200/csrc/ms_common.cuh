@@ -7,7 +7,7 @@
 #include "../../include/ms_b200.h"
 
 extern int64_t g_ms_launches;
-extern char g_ms_last_error[256];
+extern thread_local char g_ms_last_error[256];
 
 #define MS_CUDA_CHECK(expr)                                                                    \
     do {                                                                                       \
@@ -18,7 +18,7 @@ extern char g_ms_last_error[256];
         }                                                                                      \
     } while (0)
 
-#define MS_COUNT_LAUNCH() (++g_ms_launches)
+#define MS_COUNT_LAUNCH() ((void)__atomic_fetch_add(&g_ms_launches, 1, __ATOMIC_RELAXED))
 
 // ---- per-byte flags on a 32-bit word (4 bytes), result has 0x80 in each matching byte ------
 __device__ __forceinline__ uint32_t ms_eq_flags(uint32_t w, uint32_t rep) {
