@@ -626,9 +626,42 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 #define PARSE_MAX_CHUNKS 32
 #define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
 
+#ifndef MS_EXP_UNUM
+#define MS_EXP_UNUM 3
+#define MS_EXP_UDEN 4
+#endif
+// Column chunks of DECREASING width, handed out widest first (chunk-major), so that the last items a warp
+// can draw are small and the warps finish the tile together (uniform chunks left ~30 % of the warps idle at
+// the end of every tile).  The widest chunk is the END of the row: in a Devices row those are the EMG
+// columns, the longest fields.  cols[] is descending: chunk j covers columns [cols[j+1], cols[j]).
+template <typename T>
+__host__ __device__ inline int ms_chunk_table(int groups, int ncols, T* cols) {
+    const int ideal = (groups * ncols + PARSE_WARPS - 1) / PARSE_WARPS;  // column-groups per warp
+    int u = (ideal * MS_EXP_UNUM + MS_EXP_UDEN - 1) / MS_EXP_UDEN;
+    if (u < 2) u = 2;
+    int k = 0, col = 0;
+    while (col < ncols && k < PARSE_MAX_CHUNKS - 1) {
+        cols[k++] = (T)(ncols - col);
+        const int rest = ncols - col;
+        int step = (rest + 2) / 3;
+        if (step > u) step = u;
+        if (step < 1) step = 1;
+        col += step;
+    }
+    if (col < ncols) cols[k++] = (T)(ncols - col);  // cap reached: one last chunk takes the rest
+    cols[k] = 0;
+    return k;
+}
+
+// The table depends on the section (its column count) and on the number of row groups in the tile only, so the
+// host fills it in for up to PARSE_TAB_GROUPS groups: computed by one thread per tile it was a serial chain of
+// ~100 dependent instructions that every CTA waited out on a busy SM (15 % of a CTA's lifetime, measured).
+#define PARSE_TAB_GROUPS 8
 struct MsSectionsArg {
     ms_section s[MS_MAX_SECTIONS];
     int n;
+    uint16_t chunk_tab[MS_MAX_SECTIONS][PARSE_TAB_GROUPS][PARSE_MAX_CHUNKS + 1];
+    uint8_t chunk_cnt[MS_MAX_SECTIONS][PARSE_TAB_GROUPS];  // 0: not tabulated (too many columns for 16 bits)
 };
 
 __device__ __forceinline__ bool ms_is_delim(unsigned c) { return c == ',' || c == '\n' || c == '\r'; }
@@ -1012,30 +1045,16 @@ __global__ void __launch_bounds__(PARSE_THREADS, PARSE_MIN_CTAS)
             const int bb = min(sec_b, ba + PARSE_ROWS_CAP - 1);
             const int nrows = bb - ba + 1;
             // ---- A4. start offset of rows ba .. bb+1 (the last one closes row bb)
+            const int groups_ = (nrows + 31) >> 5;
+            const bool tabulated = groups_ <= PARSE_TAB_GROUPS && secs.chunk_cnt[si][groups_ - 1] != 0;
+            if (tabulated && tid <= PARSE_MAX_CHUNKS) s_chunk_col[tid] = secs.chunk_tab[si][groups_ - 1][tid];
             if (tid == 0) {
                 s_next_item = 0;
                 if (starts_at_t0 && ba == 0) row_start[0] = 0;
-                // Column chunks of DECREASING width, handed out widest first (chunk-major), so that the
-                // last items a warp can draw are small and the warps finish the tile together (uniform
-                // chunks left ~30 % of the warps idle at the end of every tile).  The widest chunk is
-                // the END of the row: in a Devices row those are the EMG columns, the longest fields.
-                // s_chunk_col is descending: chunk j covers columns [s_chunk_col[j+1], s_chunk_col[j]).
-                const int groups_ = (nrows + 31) >> 5;
-                const int ideal = (groups_ * ncols + PARSE_WARPS - 1) / PARSE_WARPS;  // column-groups per warp
-#ifndef MS_EXP_UNUM
-#define MS_EXP_UNUM 3
-#define MS_EXP_UDEN 4
-#endif
-                const int u = max(2, (ideal * MS_EXP_UNUM + MS_EXP_UDEN - 1) / MS_EXP_UDEN);
-                int k = 0, col = 0;
-                while (col < ncols && k < PARSE_MAX_CHUNKS - 1) {
-                    s_chunk_col[k++] = ncols - col;
-                    const int rest = ncols - col;
-                    col += max(1, min(u, (rest + 2) / 3));
-                }
-                if (col < ncols) s_chunk_col[k++] = ncols - col;  // cap reached: one last chunk takes the rest
-                s_chunk_col[k] = 0;
-                s_nchunks = k;
+                if (tabulated)
+                    s_nchunks = secs.chunk_cnt[si][groups_ - 1];
+                else
+                    s_nchunks = ms_chunk_table(groups_, ncols, s_chunk_col);
             }
             {
                 int lt = lt0;
@@ -1193,6 +1212,10 @@ extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_w
         if (s.row_end <= s.row_begin || s.num_cols <= 0) continue;  // nothing to parse
         if (!s.d_out && s.n_keep > 0) return MS_E_INVALID;
         if (s.stride < s.row_end - s.row_begin || s.n_keep < 0 || s.n_keep > s.num_cols) return MS_E_INVALID;
+        if (s.num_cols <= 65535) {
+            for (int g = 1; g <= PARSE_TAB_GROUPS; g++)
+                arg.chunk_cnt[arg.n][g - 1] = (uint8_t)ms_chunk_table(g, s.num_cols, arg.chunk_tab[arg.n][g - 1]);
+        }
         arg.s[arg.n++] = s;
     }
     if (n_tiles == 0 || arg.n == 0) return MS_OK;
