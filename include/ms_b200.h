@@ -114,6 +114,67 @@ int ms_scan_quoted(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, i
 int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
              int32_t n_sections, uint64_t* d_status, void* stream);
 
+/* ---- loader, single pass ----------------------------------------------------------------- */
+
+/* The whole of load_vicon_file below its header text (load_csv.py:96-135) in ONE launch: row terminators,
+ * blank (section separator) rows, the section a row belongs to and its index there (a decoupled look-back
+ * between thread blocks), the column count of each section from its coordinates line (reader.py:772-783),
+ * float() of every field (reader.py:940-948) and the channel-major float64 blocks (aggregator.py:96-124,
+ * user_data.py:391-396).  Every CSV byte is read from HBM once, every kept double written once.
+ *
+ * It answers for well-formed files only (two sections, at most one trailing blank row, no quote characters
+ * in the data rows, rows of at most MS_MAX_ROW_BYTES, outputs that fit the arena): anything else sets a bit
+ * in ms_load_result.flags, the arrays are then meaningless and the caller runs ms_scan / ms_parse, which
+ * reproduce the reference's behaviour - its errors included - on every input. */
+#define MS_LOAD_PEEK 8192 /* bytes of header text copied out per section */
+
+/* ms_load_result.flags */
+#define MS_LOAD_ROW_TOO_LONG 1u  /* a row does not end within MS_MAX_ROW_BYTES of the end of its tile */
+#define MS_LOAD_DENSE_ROWS 2u    /* too many rows start in one tile */
+#define MS_LOAD_MANY_BLANKS 4u   /* more than two blank rows in one tile */
+#define MS_LOAD_TAIL_ROWS 8u     /* rows after the second blank row (the reference raises there) */
+#define MS_LOAD_OVERFLOW 16u     /* a section does not fit the arena / its row capacity */
+#define MS_LOAD_BAD_HEADER 32u   /* a coordinates line with fewer than 3 fields (or more than 65535) */
+#define MS_LOAD_HIGH_BYTES 64u   /* some byte >= 0x80 next to a line end, quote or blank (the only ones looked at) */
+/* ms_load_result.have */
+#define MS_LOAD_HAVE_HEADER0 1u  /* << section: header_offset / peek_bytes are set */
+#define MS_LOAD_HAVE_DESC0 4u    /* << section: num_cols / n_keep / stride / out_offset are set */
+#define MS_LOAD_HAVE_ROWS0 16u   /* << section: data_rows is set */
+
+typedef struct ms_load_plan {
+    double* d_arena;      /* device memory for both sections' blocks, 16-byte aligned */
+    int64_t arena_elems;  /* doubles in the arena */
+    int64_t cap_rows[2];  /* row capacity (= channel stride) of each section's block; cap_rows[1] == 0: the
+                             second block takes what the first one leaves of the arena */
+    int32_t tile_bytes;   /* CSV bytes per thread block, a multiple of 16 in [4096, MS_TILE_BYTES]; 0 = MS_TILE_BYTES.
+                             Fewest idle lanes when a tile holds just under a multiple of 32 rows. */
+    int32_t reserved;
+} ms_load_plan;
+
+/* Written to DEVICE memory; copy it back after the stream is done. */
+typedef struct ms_load_result {
+    uint64_t status;           /* as ms_parse: MS_ERR_NONE, or (byte offset << 3) | kind of the first bad field */
+    uint32_t flags;            /* MS_LOAD_*: non-zero = not a file for this entry point */
+    uint32_t have;             /* MS_LOAD_HAVE_* */
+    uint32_t n_blank_rows;     /* blank rows in the file, saturating at 3 */
+    uint32_t reserved;
+    int64_t tail_rows;         /* csv rows after the last blank row (all rows if there is none) */
+    int64_t n_quotes;          /* '"' bytes next to a line end or blank, plus every one the parser met */
+    int64_t header_offset[2];  /* byte offset of the section's first header line */
+    int64_t peek_bytes[2];     /* bytes of header text copied to d_peek + section * MS_LOAD_PEEK */
+    int64_t blank_end[2];      /* offset of the last byte of the blank row that closes the section */
+    int64_t data_rows[2];      /* data rows of the section (negative: it ended inside its header) */
+    int32_t num_cols[2];       /* fields parsed per row */
+    int32_t n_keep[2];         /* channels stored: num_cols - 2 */
+    int64_t stride[2];         /* elements between channels of the section's block */
+    int64_t out_offset[2];     /* element offset of the block in the arena: block[c * stride + row] */
+} ms_load_result;
+
+int64_t ms_load_workspace_bytes(int64_t n_bytes, int32_t tile_bytes);
+/* d_bytes as for ms_scan; d_workspace: ms_load_workspace_bytes(), 16-byte aligned; d_peek: 2 * MS_LOAD_PEEK bytes. */
+int ms_load_fused(const uint8_t* d_bytes, int64_t n_bytes, const ms_load_plan* h_plan, void* d_workspace,
+                  int64_t workspace_bytes, ms_load_result* d_result, uint8_t* d_peek, void* stream);
+
 /* ---- windowing ------------------------------------------------------------------------ */
 
 /* _transition_indices (segment.py:667-755): alternating search for the first run of
@@ -202,6 +263,10 @@ int ms_nmf_mu_stream(const float* d_X, int64_t n, int32_t m, const int32_t* h_ra
                      void* d_work, int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
 
 /* ---- misc ------------------------------------------------------------------------------- */
+/* The used part of a channel-major block (rows channels of width_bytes each, src_pitch_bytes apart) to host
+ * memory as one 2-D copy on the DMA engine; asynchronous when h_dst is page-locked. */
+int ms_copy_rows_to_host(void* h_dst, int64_t dst_pitch_bytes, const void* d_src, int64_t src_pitch_bytes,
+                         int64_t width_bytes, int64_t rows, void* stream);
 /* Text of the last CUDA failure reported (MS_E_CUDA) to the calling thread. */
 const char* ms_last_cuda_error(void);
 const char* ms_version(void);

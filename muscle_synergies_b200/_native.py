@@ -49,6 +49,44 @@ class Section(ctypes.Structure):
     ]
 
 
+MS_LOAD_PEEK = 8192
+MS_LOAD_HAVE_HEADER0 = 1
+MS_LOAD_HAVE_DESC0 = 4
+MS_LOAD_HAVE_ROWS0 = 16
+MS_LOAD_FLAG_NAMES = {1: "ROW_TOO_LONG", 2: "DENSE_ROWS", 4: "MANY_BLANKS", 8: "TAIL_ROWS", 16: "OVERFLOW",
+                      32: "BAD_HEADER", 64: "HIGH_BYTES"}
+
+
+class LoadPlan(ctypes.Structure):
+    _fields_ = [
+        ("d_arena", ctypes.c_void_p),
+        ("arena_elems", ctypes.c_int64),
+        ("cap_rows", ctypes.c_int64 * 2),
+        ("tile_bytes", ctypes.c_int32),
+        ("reserved", ctypes.c_int32),
+    ]
+
+
+class LoadResult(ctypes.Structure):
+    _fields_ = [
+        ("status", ctypes.c_uint64),
+        ("flags", ctypes.c_uint32),
+        ("have", ctypes.c_uint32),
+        ("n_blank_rows", ctypes.c_uint32),
+        ("reserved", ctypes.c_uint32),
+        ("tail_rows", ctypes.c_int64),
+        ("n_quotes", ctypes.c_int64),
+        ("header_offset", ctypes.c_int64 * 2),
+        ("peek_bytes", ctypes.c_int64 * 2),
+        ("blank_end", ctypes.c_int64 * 2),
+        ("data_rows", ctypes.c_int64 * 2),
+        ("num_cols", ctypes.c_int32 * 2),
+        ("n_keep", ctypes.c_int32 * 2),
+        ("stride", ctypes.c_int64 * 2),
+        ("out_offset", ctypes.c_int64 * 2),
+    ]
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -81,6 +119,9 @@ def _declare(L):
         "ms_nmf_stream_workspace_bytes": (i64, [i32, i32]),
         "ms_nmf_mu_stream": (ctypes.c_int, [vp, i64, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, vp, i32,
                                             ctypes.c_float, i32, vp, vp, vp, vp, vp]),
+        "ms_load_workspace_bytes": (i64, [i64, i32]),
+        "ms_load_fused": (ctypes.c_int, [vp, i64, ctypes.POINTER(LoadPlan), vp, i64, vp, vp, vp]),
+        "ms_copy_rows_to_host": (ctypes.c_int, [vp, i64, vp, i64, i64, i64, vp]),
         "ms_last_cuda_error": (ctypes.c_char_p, []),
         "ms_version": (ctypes.c_char_p, []),
         "ms_launch_count": (i64, []),

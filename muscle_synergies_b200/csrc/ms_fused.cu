@@ -1,0 +1,655 @@
+// Single-pass Vicon Nexus CSV loader for sm_100a: ms_load_kernel.
+//
+// One launch takes the CSV bytes to the channel-major float64 blocks of both sections.  Every byte is read from
+// HBM once (one TMA bulk copy per tile into shared memory) and classified once; every kept double is written
+// once.  What the two-pass path (ms_loader.cu: ms_scan -> host -> ms_parse) settled between its passes is
+// settled inside the launch:
+//
+//   * the csv row index of a tile's first row: a decoupled look-back over per-tile words that carry
+//     {blank rows so far, rows since the last blank row} - which is all a row needs to know about the rows
+//     before it: its section (reader.py:971-987 switches section at a blank row) and its index in the section
+//     (lines 0-4 are the header, reader.py:250-835; line i >= 5 is data row i - 5);
+//   * the column count of a section: the tile that owns the section's coordinates line (line 3) counts its
+//     fields the way CoordinatesState does (strip, drop trailing blanks: reader.py:772-783), carves the
+//     section's block out of the caller's arena and publishes a descriptor the later tiles wait for;
+//   * the header text of both sections is copied out for the host (names, units, frequencies are host work).
+//
+// The kernel only promises results for well-formed input - two sections, at most one trailing blank row, no
+// quotes, rows that fit the tile overhang, outputs that fit the arena.  Anything else raises a flag in
+// ms_load_result.flags and the caller runs the two-pass path, which reproduces the reference's behaviour
+// (and its errors) in full.  Replaces, per data row, reader.py:886-948, aggregator.py:96-124, 229-241,
+// user_data.py:391-396.
+#include <stdio.h>
+
+#include "ms_field.cuh"
+
+#define FUSED_THREADS PARSE_THREADS
+#define FUSED_WARPS (FUSED_THREADS / 32)
+#define FUSED_MAX_TILE MS_TILE_BYTES
+#define FUSED_MAX_REGION (FUSED_MAX_TILE + MS_MAX_ROW_BYTES)
+#define FUSED_MAX_NSEG (FUSED_MAX_REGION / 16)
+#define FUSED_PAD 16
+#define FUSED_BYTES_SMEM (FUSED_MAX_REGION + 2 * FUSED_PAD)
+#define FUSED_ROWS_CAP 1024  // rows that may start in one tile
+#define FUSED_HIT_WORDS (FUSED_MAX_NSEG / 32 + 2)
+// dynamic shared memory: staged bytes | comma masks | terminator masks | hit bitmap | row starts
+#define FUSED_OFF_CMASK FUSED_BYTES_SMEM
+#define FUSED_OFF_TMASK (FUSED_OFF_CMASK + FUSED_MAX_NSEG * 2 + 16)
+#define FUSED_OFF_HIT (FUSED_OFF_TMASK + FUSED_MAX_NSEG * 2)
+#define FUSED_OFF_ROWS (FUSED_OFF_HIT + FUSED_HIT_WORDS * 4)
+#define FUSED_SMEM (FUSED_OFF_ROWS + (FUSED_ROWS_CAP + 2) * 2 + 12)
+static_assert(FUSED_OFF_CMASK % 16 == 0 && FUSED_OFF_TMASK % 16 == 0 && FUSED_OFF_HIT % 8 == 0 && FUSED_OFF_ROWS % 4 == 0,
+              "shared memory layout");
+static_assert(FUSED_MAX_REGION + FUSED_PAD < 65536, "row starts are 16-bit");
+
+// ---- workspace: everything the tiles tell each other (zeroed before the launch) -----------------------------
+struct MsSecDesc {
+    uint32_t ready;    // 1 once the fields below are valid (written last, release)
+    int32_t num_cols;  // fields parsed per row
+    int32_t n_keep;    // channels stored: num_cols - 2
+    int32_t pad;
+    long long stride;      // elements between channels
+    long long out_offset;  // element offset of the block in the arena
+    uint16_t chunk_tab[PARSE_TAB_GROUPS][PARSE_MAX_CHUNKS + 1];
+    uint8_t chunk_cnt[PARSE_TAB_GROUPS];
+};
+struct MsFusedWs {
+    uint32_t ticket;  // tile ids are handed out in launch order: a tile's predecessors are running or done
+    uint32_t pad[15];
+    MsSecDesc desc[2];
+    // look-back words follow (8 bytes per tile)
+};
+#define FUSED_LB_OFFSET ((int64_t)((sizeof(MsFusedWs) + 255) / 256 * 256))
+
+// look-back word: [63:62] state, [61:60] blank rows (saturating at 3), [59:0] rows since the last blank row
+#define LB_INVALID 0ull
+#define LB_AGGREGATE 1ull
+#define LB_INCLUSIVE 2ull
+struct LbVal {
+    uint32_t nb;
+    unsigned long long dist;
+};
+__device__ __forceinline__ unsigned long long lb_pack(unsigned long long state, LbVal v) {
+    return (state << 62) | ((unsigned long long)(v.nb > 3u ? 3u : v.nb) << 60) | (v.dist & ((1ull << 60) - 1ull));
+}
+__device__ __forceinline__ LbVal lb_unpack(unsigned long long w) {
+    LbVal v;
+    v.nb = (uint32_t)(w >> 60) & 3u;
+    v.dist = w & ((1ull << 60) - 1ull);
+    return v;
+}
+// state after `left` followed by `right`
+__device__ __forceinline__ LbVal lb_combine(LbVal left, LbVal right) {
+    LbVal r;
+    if (right.nb) {
+        r.nb = min(3u, left.nb + right.nb);
+        r.dist = right.dist;
+    } else {
+        r.nb = left.nb;
+        r.dist = left.dist + right.dist;
+    }
+    return r;
+}
+__device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_u32(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.gpu.global.u32 [%0], %1;\n" ::"l"(p), "r"(v) : "memory");
+}
+
+struct MsFusedArgs {
+    double* arena;
+    long long arena_elems;
+    long long cap_rows[2];
+    int tile_bytes;
+    int region_bytes;  // tile_bytes + MS_MAX_ROW_BYTES
+    long long n_tiles;
+};
+
+__global__ void __launch_bounds__(FUSED_THREADS, 3)
+    ms_load_kernel(const uint8_t* __restrict__ src, long long n, MsFusedWs* __restrict__ ws, const MsFusedArgs args,
+                   ms_load_result* __restrict__ res, uint8_t* __restrict__ peek) {
+    extern __shared__ __align__(16) uint8_t smem_raw[];
+    uint8_t* const reg = smem_raw + FUSED_PAD;  // reg[i] = src[t0 + i]
+    uint16_t* const cmask = reinterpret_cast<uint16_t*>(smem_raw + FUSED_OFF_CMASK);  // commas per 16-byte segment
+    uint16_t* const tmask = reinterpret_cast<uint16_t*>(smem_raw + FUSED_OFF_TMASK);  // terminator ends, hit segments only
+    uint32_t* const hitmap = reinterpret_cast<uint32_t*>(smem_raw + FUSED_OFF_HIT);   // segments with a byte < 0x23 or >= 0x80
+    uint16_t* const row_start = reinterpret_cast<uint16_t*>(smem_raw + FUSED_OFF_ROWS);  // [L]: first byte of local row L
+    __shared__ int s_warp_terms[FUSED_WARPS];
+    __shared__ int s_lt_end, s_next_item, s_nchunks, s_nblank, s_blank_lo, s_blank_hi, s_quotes, s_stop;
+    __shared__ uint32_t s_tile, s_flags, s_pre_nb;
+    __shared__ unsigned long long s_pre_dist;
+    __shared__ int s_q, s_commas;
+    __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
+    __shared__ __align__(8) unsigned long long s_stage_bar;
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    unsigned long long* const lb = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + FUSED_LB_OFFSET);
+
+    if (tid == 0) {
+        s_tile = atomicAdd(&ws->ticket, 1u);
+        s_lt_end = -1;
+        s_nblank = 0;
+        s_blank_lo = 0x7fffffff;
+        s_blank_hi = -1;
+        s_quotes = 0;
+        s_flags = 0;
+        s_stop = 0;
+    }
+    __syncthreads();
+    const long long tile = (long long)s_tile;
+    const int tile_bytes = args.tile_bytes, region = args.region_bytes;
+    const long long t0 = tile * (long long)tile_bytes;
+    const int tile_len = (int)min((long long)tile_bytes, n - t0);
+    const int nseg = region >> 4;
+
+    // ---- P0. stage [t0 - 16, t0 + region + 16) in shared memory; beyond either end of the file: '\n'.
+    // One bulk asynchronous copy (cp.async.bulk: the TMA engine, SASS UBLKCP) issued by one thread moves every whole
+    // 16-byte chunk inside the buffer and completes on an mbarrier; chunks at the edges of the file are filled by hand.
+    const long long off0 = t0 - FUSED_PAD;
+    const int n_chunks_smem = (region + 2 * FUSED_PAD) >> 4;
+    const int lo_chunk = off0 < 0 ? (int)((-off0) >> 4) : 0;
+    const long long whole = (n >> 4) - (off0 >> 4);  // chunks that end at or before byte n
+    const int hi_chunk = (int)max((long long)lo_chunk, min((long long)n_chunks_smem, whole));
+    if (tid == 0) {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+        const uint32_t bytes = (uint32_t)(hi_chunk - lo_chunk) * 16u;
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;\n" ::"r"(bar) : "memory");
+        asm volatile("fence.mbarrier_init.release.cluster;\n" ::: "memory");
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;\n" ::"r"(bar), "r"(bytes) : "memory");
+        if (bytes) {
+            const uint32_t dst = (uint32_t)__cvta_generic_to_shared(smem_raw + lo_chunk * 16);
+            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];\n" ::"r"(dst),
+                         "l"(src + off0 + (long long)lo_chunk * 16), "r"(bytes), "r"(bar)
+                         : "memory");
+        }
+    }
+    for (int i = tid; i < n_chunks_smem; i += FUSED_THREADS) {
+        if (i >= lo_chunk && i < hi_chunk) {
+            if (lo_chunk == 0 && hi_chunk == n_chunks_smem) break;  // the usual tile: nothing by hand
+            continue;
+        }
+        const long long off = off0 + (long long)i * 16;
+        uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
+        if (off >= 0 && off < n) {
+            // the chunk that holds byte n: the allocation is readable up to n rounded up to 16 (ABI requirement)
+            const uint4 r = __ldg(reinterpret_cast<const uint4*>(src + off));
+            const uint32_t rw[4] = {r.x, r.y, r.z, r.w};
+            uint32_t w[4];
+            const int valid = (int)(n - off);
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                const int have = valid - 4 * k;
+                if (have >= 4)
+                    w[k] = rw[k];
+                else if (have > 0) {
+                    const uint32_t m = (1u << (8 * have)) - 1u;
+                    w[k] = (rw[k] & m) | (0x0a0a0a0au & ~m);
+                } else
+                    w[k] = 0x0a0a0a0au;
+            }
+            v = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        *reinterpret_cast<uint4*>(smem_raw + i * 16) = v;
+    }
+    if (tid < 2) hitmap[(nseg >> 5) + tid] = 0;  // the words a thread's hit window may reach past the last segment
+    __syncthreads();  // mbarrier init and the hand-filled chunks are visible
+    {
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+    }
+
+    // ---- P1a. every 16-byte segment once, lanes on consecutive segments: comma mask (exact) and a quick test for
+    // "some byte is below 0x23 or above 0x7f" - line ends, quotes, blanks, control and non-ASCII bytes; a data row has
+    // one or two such segments, the rest is digits, signs, points and commas.  (w - 0x23..) | w has bit 7 of a byte set
+    // for every such byte; a borrow can only add a false hit on a '#' that follows one.
+    for (int base = 0; base < nseg; base += FUSED_THREADS) {
+        const int v = base + tid;
+        const bool in = v < nseg;
+        uint32_t ctrl = 0, cm = 0;
+        if (in) {
+            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+            for (int k = 0; k < 4; k++) {
+                ctrl |= (w[k] - 0x23232323u) | w[k];
+                cm |= ms_gather4(ms_eq_flags(w[k], 0x2c2c2c2cu)) << (4 * k);
+            }
+            cmask[v] = (uint16_t)cm;
+        }
+        const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
+        if (lane == 0 && v < nseg) hitmap[v >> 5] = hits;
+    }
+    __syncthreads();
+
+    // ---- P1b. a thread owns a run of consecutive segments; the exact line ends of those the quick test hit
+    // (universal newlines: '\n', "\r\n", lone '\r' - what open(filename) gives csv.reader, load_csv.py:29)
+    const int vpt = (nseg + FUSED_THREADS - 1) / FUSED_THREADS;  // segments per thread, <= 7
+    const int v0 = tid * vpt;
+    uint32_t my_hits = 0;
+    if (v0 < nseg) {
+        const uint32_t h0 = hitmap[v0 >> 5], h1 = hitmap[(v0 >> 5) + 1];
+        my_hits = __funnelshift_r(h0, h1, v0 & 31) & ((1u << vpt) - 1u);
+    }
+    int my_terms = 0, my_quotes = 0;
+    uint32_t my_flags = 0;
+    int lt_end_part = -1;  // terminators of my segments before position tile_len - 1, if that position is mine
+    {
+        const int q = tile_len - 1;
+        const bool mine = q >= (v0 << 4) && q < ((v0 + vpt) << 4);
+        if (mine) lt_end_part = 0;
+        uint32_t hb = my_hits;
+        while (hb) {
+            const int k = __ffs(hb) - 1;
+            hb &= hb - 1u;
+            const int v = v0 + k;
+            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+            const uint32_t lf = ms_mask16(ms_eq_flags(x.x, 0x0a0a0a0au), ms_eq_flags(x.y, 0x0a0a0a0au),
+                                          ms_eq_flags(x.z, 0x0a0a0a0au), ms_eq_flags(x.w, 0x0a0a0a0au));
+            const uint32_t cr = ms_mask16(ms_eq_flags(x.x, 0x0d0d0d0du), ms_eq_flags(x.y, 0x0d0d0d0du),
+                                          ms_eq_flags(x.z, 0x0d0d0d0du), ms_eq_flags(x.w, 0x0d0d0d0du));
+            my_quotes += __popc(ms_eq_flags(x.x, 0x22222222u)) + __popc(ms_eq_flags(x.y, 0x22222222u)) +
+                         __popc(ms_eq_flags(x.z, 0x22222222u)) + __popc(ms_eq_flags(x.w, 0x22222222u));
+            if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
+            const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
+            tmask[v] = (uint16_t)term;
+            my_terms += __popc(term);
+            if (mine) {
+                const int p0 = v << 4;
+                if (q >= p0 + 16)
+                    lt_end_part += __popc(term);
+                else if (q > p0)
+                    lt_end_part += __popc(term & ((1u << (q - p0)) - 1u));
+            }
+        }
+    }
+    // block-wide exclusive prefix sum of the terminator counts
+    int inc = my_terms;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp_terms[warp] = inc;
+    if (my_quotes) atomicAdd(&s_quotes, my_quotes);
+    if (my_flags) atomicOr(&s_flags, my_flags);
+    __syncthreads();
+    int before = 0, total_terms = 0;
+#pragma unroll
+    for (int w = 0; w < FUSED_WARPS; w++) {
+        const int c = s_warp_terms[w];
+        if (w < warp) before += c;
+        total_terms += c;
+    }
+    const int lt0 = before + inc - my_terms;  // terminators before my segments
+    if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
+    // local row L starts right after the L-th terminator of the region (L >= 1); row 0 starts at byte 0
+    {
+        int lt = lt0;
+        uint32_t hb = my_hits;
+        while (hb) {
+            const int k = __ffs(hb) - 1;
+            hb &= hb - 1u;
+            const int v = v0 + k;
+            uint32_t term = tmask[v];
+            while (term) {
+                const int b = __ffs(term) - 1;
+                term &= term - 1u;
+                lt++;
+                if (lt <= FUSED_ROWS_CAP + 1) row_start[lt] = (uint16_t)((v << 4) + b + 1);
+            }
+        }
+        if (tid == 0) row_start[0] = 0;
+    }
+    __syncthreads();
+
+    // ---- ownership: the rows that START in [t0, t0 + tile_len)
+    const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
+    const int lt_first = starts_at_t0 ? 0 : 1;
+    const int lt_last = s_lt_end;  // inclusive; tile_len >= 1, so some thread set it
+    int n_own = lt_last - lt_first + 1;
+    if (n_own < 0) n_own = 0;
+    uint32_t fatal = 0;  // conditions under which this tile cannot tell its rows apart
+    if (n_own > 0 && total_terms < lt_last + 1) fatal |= MS_LOAD_ROW_TOO_LONG;  // the last owned row does not end in the region
+    if (lt_last + 1 > FUSED_ROWS_CAP) fatal |= MS_LOAD_DENSE_ROWS;
+
+    // ---- P2. blank rows (section separators): every field empty after str.strip() (reader.py:886-901).  A data
+    // row starts with its frame number, so only rows that start with a comma or a blank are looked at in full.
+    if (!fatal) {
+        for (int L = lt_first + tid; L <= lt_last; L += FUSED_THREADS) {
+            const int p = row_start[L], e = row_start[L + 1];
+            const unsigned c = reg[p];
+            if (c == ',' || c <= 0x20u) {
+                bool blank = true;
+                for (int i = p; i < e; i++) {
+                    const unsigned b = reg[i];
+                    if (!(b == ',' || ms_is_strip_space(b))) {
+                        blank = false;
+                        break;
+                    }
+                }
+                if (blank) {
+                    atomicAdd(&s_nblank, 1);
+                    atomicMin(&s_blank_lo, L);
+                    atomicMax(&s_blank_hi, L);
+                }
+            }
+        }
+    }
+    __syncthreads();
+    const int nb = s_nblank;
+    const int blank_lo = s_blank_lo, blank_hi = s_blank_hi;
+
+    // ---- P3. publish what this tile adds, look back for what came before it
+    if (warp == 0) {
+        LbVal agg;
+        agg.nb = (uint32_t)min(nb, 3);
+        agg.dist = (unsigned long long)(nb ? lt_last - blank_hi : n_own);
+        LbVal pre;
+        pre.nb = 0;
+        pre.dist = 0;
+        if (tile > 0) {
+            if (lane == 0) st_release_u64(&lb[tile], lb_pack(LB_AGGREGATE, agg));
+            long long j = tile - 1;
+            for (;;) {
+                const long long idx = j - lane;
+                unsigned long long w = LB_INCLUSIVE << 62;  // before the first tile: nothing (no blank rows, no rows)
+                if (idx >= 0) w = ld_acquire_u64(&lb[idx]);
+                const uint32_t state = (uint32_t)(w >> 62);
+                const uint32_t invalid = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INVALID);
+                const uint32_t inclusive = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INCLUSIVE);
+                const int count = inclusive ? __ffs(inclusive) : 32;  // lanes 0 .. count-1 are what is needed
+                const uint32_t need = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
+                if (invalid & need) {
+                    __nanosleep(40);
+                    continue;
+                }
+                LbVal val = lb_unpack(w);
+#pragma unroll
+                for (int d = 1; d < 32; d <<= 1) {
+                    LbVal o;
+                    o.nb = __shfl_down_sync(0xffffffffu, val.nb, d);
+                    o.dist = __shfl_down_sync(0xffffffffu, val.dist, d);
+                    if (lane + d < count) val = lb_combine(o, val);
+                }
+                // lane 0: the tiles j - count + 1 .. j; they come before what was gathered so far
+                pre = lb_combine(val, pre);
+                if (inclusive) break;
+                j -= 32;
+            }
+            pre.nb = __shfl_sync(0xffffffffu, pre.nb, 0);
+            pre.dist = __shfl_sync(0xffffffffu, pre.dist, 0);
+        }
+        if (lane == 0) {
+            const LbVal incl = lb_combine(pre, agg);
+            st_release_u64(&lb[tile], lb_pack(LB_INCLUSIVE, incl));
+            s_pre_nb = pre.nb;
+            s_pre_dist = pre.dist;
+            if (tile == args.n_tiles - 1) {
+                // the state at the end of the file
+                res->n_blank_rows = incl.nb;
+                res->tail_rows = (long long)incl.dist;
+                if (incl.nb < 2u) {
+                    res->data_rows[incl.nb] = (long long)incl.dist - 5;
+                    atomicOr(&res->have, MS_LOAD_HAVE_ROWS0 << incl.nb);
+                }
+            }
+        }
+    }
+    if (tid == 0) {
+        if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
+        const uint32_t f = s_flags | fatal | (nb > 2 ? MS_LOAD_MANY_BLANKS : 0u);
+        if (f) atomicOr(&res->flags, f);
+    }
+    __syncthreads();
+    if (fatal) return;
+    const int pre_nb = (int)s_pre_nb;
+    const long long pre_dist = (long long)s_pre_dist;
+
+    // ---- P4. the runs of rows between this tile's blank rows: header lines, then data rows
+    const int n_cut = min(nb, 2);
+    for (int run = 0; run <= n_cut; run++) {
+        const int lo = run == 0 ? lt_first : (run == 1 ? blank_lo : blank_hi) + 1;
+        const int hi = run < n_cut ? (run == 0 ? blank_lo : blank_hi) - 1 : lt_last;
+        const int sec = pre_nb + run;
+        const long long idx_lo = run == 0 ? pre_dist : 0;  // index in its section of local row `lo`
+        if (run < n_cut && sec < 2 && tid == 0) {
+            // the blank row that closes this run closes section `sec`
+            const int Lb = run == 0 ? blank_lo : blank_hi;
+            res->data_rows[sec] = idx_lo + (Lb - lo) - 5;
+            res->blank_end[sec] = t0 + row_start[Lb + 1] - 1;
+            atomicOr(&res->have, MS_LOAD_HAVE_ROWS0 << sec);
+        }
+        if (lo > hi) continue;
+        if (sec >= 2) {
+            if (tid == 0) atomicOr(&res->flags, MS_LOAD_TAIL_ROWS);  // rows after the second blank row (Appendix C)
+            continue;
+        }
+        MsSecDesc* const desc = &ws->desc[sec];
+        // header line 0: where the section's header text starts; copy it out for the host
+        if (idx_lo == 0) {
+            const long long off = t0 + row_start[lo];
+            const long long cnt = min((long long)MS_LOAD_PEEK, n - off);
+            for (long long i = tid; i < cnt; i += FUSED_THREADS) peek[(long long)sec * MS_LOAD_PEEK + i] = src[off + i];
+            if (tid == 0) {
+                res->header_offset[sec] = off;
+                res->peek_bytes[sec] = cnt;
+                atomicOr(&res->have, MS_LOAD_HAVE_HEADER0 << sec);
+            }
+        }
+        // header line 3 (coordinates): its field count is the section's column count (reader.py:772-783)
+        if (idx_lo <= 3 && lo + (3 - idx_lo) <= hi) {
+            const int L3 = lo + (int)(3 - idx_lo);
+            const int p = row_start[L3], e = row_start[L3 + 1];
+            if (tid == 0) {
+                s_q = -1;
+                s_commas = 0;
+            }
+            __syncthreads();
+            int q = -1;
+            for (int i = p + tid; i < e; i += FUSED_THREADS) {
+                const unsigned b = reg[i];
+                if (!(b == ',' || ms_is_strip_space(b))) q = i;
+            }
+            if (q >= 0) atomicMax(&s_q, q);
+            __syncthreads();
+            const int last = s_q;  // last byte of the last non-blank field
+            int commas = 0;
+            for (int i = p + tid; i < last; i += FUSED_THREADS) commas += reg[i] == ',';
+            if (commas) atomicAdd(&s_commas, commas);
+            __syncthreads();
+            const int ncols = last >= 0 ? s_commas + 1 : 0;
+            const int keep = ncols - 2;
+            if (tid < PARSE_TAB_GROUPS && ncols > 0 && ncols <= 65535)
+                desc->chunk_cnt[tid] = (uint8_t)ms_chunk_table(tid + 1, ncols, desc->chunk_tab[tid]);
+            __syncthreads();
+            if (tid == 0) {
+                long long offset = 0, stride = args.cap_rows[sec];
+                bool ok = keep >= 1 && ncols <= 65535;
+                if (ok && sec == 1) {
+                    // behind the first section's block; its descriptor was published by an earlier tile (or above)
+                    const MsSecDesc* d0 = &ws->desc[0];
+                    while (!ld_acquire_u32(&d0->ready)) {
+                        if (*(volatile uint32_t*)&res->flags) {
+                            ok = false;
+                            break;
+                        }
+                        __nanosleep(100);
+                    }
+                    if (ok) {
+                        offset = (__ldcg(&d0->stride) * __ldcg(&d0->n_keep) + 1) & ~1ll;
+                        if (stride <= 0) stride = ((args.arena_elems - offset) / keep) & ~1ll;
+                    }
+                }
+                if (ok && (stride <= 0 || offset + stride * keep > args.arena_elems)) {
+                    atomicOr(&res->flags, MS_LOAD_OVERFLOW);
+                    ok = false;
+                }
+                if (!ok && !*(volatile uint32_t*)&res->flags) atomicOr(&res->flags, MS_LOAD_BAD_HEADER);
+                if (ok) {
+                    desc->num_cols = ncols;
+                    desc->n_keep = keep;
+                    desc->stride = stride;
+                    desc->out_offset = offset;
+                    res->num_cols[sec] = ncols;
+                    res->n_keep[sec] = keep;
+                    res->stride[sec] = stride;
+                    res->out_offset[sec] = offset;
+                    atomicOr(&res->have, MS_LOAD_HAVE_DESC0 << sec);
+                    __threadfence();
+                    st_release_u32(&desc->ready, 1u);
+                }
+            }
+        }
+        // data rows: lines 5.. of the section
+        const int Ld = lo + (int)max(0ll, 5 - idx_lo);
+        if (Ld > hi) continue;
+        if (tid == 0) {
+            int stop = 0;
+            while (!ld_acquire_u32(&desc->ready)) {
+                if (*(volatile uint32_t*)&res->flags) {  // the tile that owns the header gave up: so does the caller
+                    stop = 1;
+                    break;
+                }
+                __nanosleep(100);
+            }
+            s_stop = stop;
+        }
+        __syncthreads();
+        if (s_stop) return;
+        const int ncols = __ldcg(&desc->num_cols);
+        const int n_keep = __ldcg(&desc->n_keep);
+        const long long out_stride = __ldcg(&desc->stride);
+        double* const out_base = args.arena + __ldcg(&desc->out_offset);
+        const int nrows = hi - Ld + 1;
+        const long long out_row0 = idx_lo + (Ld - lo) - 5;  // output row of local row Ld
+        if (out_row0 + nrows > out_stride) {
+            if (tid == 0) atomicOr(&res->flags, MS_LOAD_OVERFLOW);
+            continue;
+        }
+        const int groups = (nrows + 31) >> 5;
+        const bool tabulated = groups <= PARSE_TAB_GROUPS && __ldcg(&desc->chunk_cnt[groups - 1]) != 0;
+        if (tabulated && tid <= PARSE_MAX_CHUNKS) s_chunk_col[tid] = __ldcg(&desc->chunk_tab[groups - 1][tid]);
+        if (tid == 0) {
+            s_next_item = 0;
+            if (tabulated)
+                s_nchunks = __ldcg(&desc->chunk_cnt[groups - 1]);
+            else
+                s_nchunks = ms_chunk_table(groups, ncols, s_chunk_col);
+        }
+        __syncthreads();
+
+        // lanes = rows, in lockstep over the columns of a chunk; warps draw (row group, column chunk) items
+        const int nchunks = s_nchunks;
+        const int items = groups * nchunks;
+        const uint32_t inv_groups = (65536u + groups - 1) / groups;  // item / groups by multiply-shift (items < 2^10)
+        unsigned long long* const status = reinterpret_cast<unsigned long long*>(&res->status);
+        for (;;) {
+            int item = 0;
+            if (lane == 0) item = atomicAdd(&s_next_item, 1);
+            item = __shfl_sync(0xffffffffu, item, 0);
+            if (item >= items) break;
+            const int k = (int)(((uint32_t)item * inv_groups) >> 16), g = item - k * groups;  // chunk-major: wide chunks first
+            const int r = (g << 5) + lane;
+            if (r < nrows) {
+                const int c_lo = s_chunk_col[k + 1], c_hi = s_chunk_col[k];
+                int p = row_start[Ld + r];
+                bool done = false;
+                if (c_lo > 0) {
+                    // first byte of column c_lo = one past the c_lo-th comma of the row, if the row has it
+                    const int row_end = row_start[Ld + r + 1];  // one past the row's terminator
+                    int seg = p >> 4;
+                    uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
+                    int need = c_lo;
+                    int cnt = __popc(m);
+                    while (cnt < need && (seg << 4) < row_end) {
+                        need -= cnt;
+                        m = cmask[++seg];
+                        cnt = __popc(m);
+                    }
+                    if (cnt < need) {
+                        done = true;
+                    } else {
+                        for (int i = 1; i < need; i++) m &= m - 1u;
+                        p = (seg << 4) + __ffs(m);  // position after that comma
+                        if (p > row_end - 1) done = true;  // the comma belongs to a later row
+                    }
+                }
+                double* out = out_base + (long long)(c_lo - 2) * out_stride + (out_row0 + r);
+                for (int c = c_lo; c < c_hi; c++, out += out_stride) {
+                    uint64_t bits = MS_NAN_BITS;
+                    if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
+                    const int ch = c - 2;
+                    if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                }
+            }
+        }
+        __syncthreads();  // s_chunk_col / s_next_item are reused by the next run
+    }
+}
+
+// ===================================================================================================
+// C ABI
+// ===================================================================================================
+static int ms_fused_tile_bytes(int32_t tile_bytes) {
+    if (tile_bytes <= 0) return FUSED_MAX_TILE;
+    int t = tile_bytes / 16 * 16;
+    if (t < 4096) t = 4096;
+    if (t > FUSED_MAX_TILE) t = FUSED_MAX_TILE;
+    return t;
+}
+
+extern "C" int64_t ms_load_workspace_bytes(int64_t n_bytes, int32_t tile_bytes) {
+    const int t = ms_fused_tile_bytes(tile_bytes);
+    const int64_t n_tiles = n_bytes <= 0 ? 0 : (n_bytes + t - 1) / t;
+    return FUSED_LB_OFFSET + (n_tiles + 1) * 8;
+}
+
+extern "C" int ms_load_fused(const uint8_t* d_bytes, int64_t n_bytes, const ms_load_plan* h_plan, void* d_workspace,
+                             int64_t workspace_bytes, ms_load_result* d_result, uint8_t* d_peek, void* stream) {
+    if (!d_bytes || !h_plan || !d_workspace || !d_result || !d_peek || n_bytes < 0) return MS_E_INVALID;
+    if (((uintptr_t)d_bytes & 15) != 0 || ((uintptr_t)d_workspace & 15) != 0) return MS_E_INVALID;
+    if (!h_plan->d_arena || h_plan->arena_elems < 0 || h_plan->cap_rows[0] <= 0 || h_plan->cap_rows[1] < 0) return MS_E_INVALID;
+    const int tile = ms_fused_tile_bytes(h_plan->tile_bytes);
+    const int64_t need = ms_load_workspace_bytes(n_bytes, tile);
+    if (workspace_bytes < need) return MS_E_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, (size_t)need, st));
+    MS_CUDA_CHECK(cudaMemsetAsync(d_result, 0, sizeof(ms_load_result), st));
+    MS_CUDA_CHECK(cudaMemsetAsync(&d_result->status, 0xFF, sizeof(uint64_t), st));
+    const int64_t n_tiles = n_bytes == 0 ? 0 : (n_bytes + tile - 1) / tile;
+    if (n_tiles == 0) return MS_OK;
+    MsFusedArgs a;
+    a.arena = h_plan->d_arena;
+    a.arena_elems = h_plan->arena_elems;
+    a.cap_rows[0] = h_plan->cap_rows[0];
+    a.cap_rows[1] = h_plan->cap_rows[1];
+    a.tile_bytes = tile;
+    a.region_bytes = tile + MS_MAX_ROW_BYTES;
+    a.n_tiles = n_tiles;
+    MS_CUDA_CHECK(cudaFuncSetAttribute(ms_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
+    ms_load_kernel<<<(unsigned)n_tiles, FUSED_THREADS, FUSED_SMEM, st>>>(d_bytes, n_bytes, (MsFusedWs*)d_workspace, a, d_result,
+                                                                          d_peek);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}

@@ -20,6 +20,29 @@ from .definitions import DeviceType, SamplingFreq
 FrameSubfr = Tuple[int, int]
 
 
+class HostLease:
+    """A pinned host buffer on loan from a loader's pool.  numpy arrays made from it (and every view of them, the
+    blocks of a DataFrame included) keep it alive; when the last one is gone the buffer goes back to the pool.
+    Nothing a caller still holds is ever overwritten by a later file."""
+
+    def __init__(self, pinned, pool, shape):
+        self.pinned = pinned
+        self.pool = pool
+        self.event = None
+        self.__array_interface__ = {
+            "data": (pinned.data_ptr(), False), "shape": tuple(shape), "typestr": "<f8", "strides": None, "version": 3,
+        }
+
+    def __del__(self):
+        try:
+            if self.event is not None:
+                self.event.synchronize()  # a copy may still be writing into it
+            if self.pool is not None and len(self.pool) < 8:
+                self.pool.append(self.pinned)
+        except Exception:  # noqa: BLE001 - interpreter shutdown
+            pass
+
+
 class SectionBlock:
     """Channel-major float64 block of one CSV section: tensor[channel, row]."""
 
@@ -27,23 +50,51 @@ class SectionBlock:
         self.tensor = tensor  # torch.float64, (n_keep, stride) on the GPU, stride >= n_rows
         self.n_rows = n_rows
         self._host = None
-        self._pending = None  # (pinned tensor, event) of an asynchronous device->host copy
+        self._pending = None  # (HostLease or pinned tensor, event) of an asynchronous device->host copy
 
-    def prefetch_host(self, stream, pinned=None):
-        """Starts the device->host copy on `stream` (optionally into a caller-owned pinned
-        buffer of at least n_keep * n_rows doubles); `host()` waits for it."""
+    def _copy_rows(self, dst_ptr: int, stream):
+        """The (n_keep, n_rows) part of the block to contiguous host memory: one 2-D DMA copy, whatever the stride."""
+        import ctypes
+
+        from .. import _native as nat
+
+        n_keep = int(self.tensor.shape[0])
+        stride = int(self.tensor.stride(0)) if n_keep > 1 else self.n_rows
+        if n_keep == 0 or self.n_rows == 0:
+            return
+        nat.check(
+            nat.lib().ms_copy_rows_to_host(dst_ptr, self.n_rows * 8, self.tensor.data_ptr(), max(stride, self.n_rows) * 8,
+                                           self.n_rows * 8, n_keep, ctypes.c_void_p(stream.cuda_stream)),
+            "ms_copy_rows_to_host",
+        )
+
+    def prefetch_host(self, stream, pinned=None, pool=None):
+        """Starts the device->host copy on `stream`; `host()` waits for it.  `pinned`: a caller-owned pinned
+        buffer of at least n_keep * n_rows doubles (valid for as long as the caller says); `pool`: a list of
+        pinned tensors to borrow from - the buffer returns to it when the last host array of this block is gone."""
         import torch
 
-        view = self.tensor[:, : self.n_rows]
+        shape = (int(self.tensor.shape[0]), self.n_rows)
+        need = max(1, shape[0] * shape[1])
+        lease = None
         if pinned is None:
-            dst = torch.empty(view.shape, dtype=view.dtype, pin_memory=True)
-        else:
-            dst = pinned[: view.numel()].view(view.shape)
-        with torch.cuda.stream(stream):
-            dst.copy_(view, non_blocking=True)
+            buf = None
+            if pool is not None:
+                for i, cand in enumerate(pool):
+                    if cand.numel() >= need:
+                        buf = pool.pop(i)
+                        break
+            if buf is None:
+                buf = torch.empty(need, dtype=torch.float64, pin_memory=True)
+            lease = HostLease(buf, pool, shape)
+            pinned = buf
+        with torch.cuda.device(self.tensor.device):
+            self._copy_rows(pinned.data_ptr(), stream)
             event = torch.cuda.Event()
             event.record(stream)
-        self._pending = (dst, event)
+        if lease is not None:
+            lease.event = event
+        self._pending = (lease if lease is not None else pinned[: shape[0] * shape[1]].view(shape), event)
 
     def host(self) -> np.ndarray:
         """(n_keep, n_rows) float64 numpy array (one device->host copy, cached)."""
@@ -51,16 +102,18 @@ class SectionBlock:
             if self._pending is not None:
                 dst, event = self._pending
                 event.synchronize()
-                self._host = dst.numpy()
+                self._host = np.asarray(dst) if isinstance(dst, HostLease) else dst.numpy()
                 self._pending = None
             else:
                 import torch
 
                 # lazily, into ordinary memory: page-locking a fresh buffer of this size costs several times the
-                # copy itself; the pipelined loaders (load_many) bring their own pinned ring instead
-                view = self.tensor[:, : self.n_rows]
-                host = np.empty(tuple(view.shape), dtype=np.float64)
-                torch.from_numpy(host).copy_(view)
+                # copy itself; the pipelined loaders (load_many) bring pooled pinned buffers instead
+                host = np.empty((int(self.tensor.shape[0]), self.n_rows), dtype=np.float64)
+                with torch.cuda.device(self.tensor.device):
+                    stream = torch.cuda.current_stream(self.tensor.device)
+                    self._copy_rows(host.ctypes.data, stream)
+                    stream.synchronize()
                 self._host = host
         return self._host
 

@@ -22,6 +22,7 @@ import contextlib
 import ctypes
 import os
 import re
+import threading
 from typing import Callable, List, Optional, Tuple
 
 import numpy as np
@@ -53,6 +54,14 @@ _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 _READ_CHUNK = 32 << 20
 _read_pool = None
+
+# Which kernels load a file: None = the single-pass kernel (ms_load_fused) with the two-pass path
+# (ms_scan -> host -> ms_parse) behind it for everything it declines; "two_pass" = the two-pass path only.
+# FORCE_TILE: CSV bytes per thread block of the single-pass kernel (tests sweep it to move tile boundaries).
+FORCE_PATH = os.environ.get("MS_B200_LOADER") or None
+FORCE_TILE = None
+_FMETA_PEEK = 256  # offset of the two header peeks behind ms_load_result in the single-pass meta buffer
+_FMETA_BYTES = _FMETA_PEEK + 2 * nat.MS_LOAD_PEEK
 
 
 def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callable[[int, int], None]] = None) -> None:
@@ -178,9 +187,21 @@ class ViconLoader:
         self._pinned_head = torch.empty(_PEEK, dtype=torch.uint8, pin_memory=True)
         self._pinned_status = torch.empty(1, dtype=torch.int64, pin_memory=True)
         self._side_streams = None  # copy-in / copy-out streams of load_many, created on first use
+        # single-pass path: what the previous file looked like (sizes the next file's arena and tile), pinned
+        # buffers on loan to results (data_model.HostLease), meta buffers, counters
+        self._history = None
+        self._host_pool = []
+        self._fmeta_pool = []
+        self.stats = {"fused": 0, "two_pass": 0, "declined": {}}
+        self._fused_skip = self._fused_backoff = 0
+        self._lock = threading.RLock()  # one load at a time per loader: its staging and meta buffers are shared
 
     # ---- public -----------------------------------------------------------------------------
     def load_file(self, csv_filename) -> ViconNexusData:
+        with self._lock, self.torch.cuda.device(self.device):
+            return self._load_file(csv_filename)
+
+    def _load_file(self, csv_filename) -> ViconNexusData:
         torch = self.torch
         size = os.path.getsize(csv_filename)  # FileNotFoundError propagates unwrapped, like open()
         staging = self._staging(size)
@@ -197,6 +218,10 @@ class ViconLoader:
 
     def load_bytes(self, data, name: str = "<bytes>") -> ViconNexusData:
         """`data`: bytes / bytearray / uint8 numpy array / uint8 CPU tensor holding the CSV."""
+        with self._lock, self.torch.cuda.device(self.device):
+            return self._load_bytes(data, name)
+
+    def _load_bytes(self, data, name: str) -> ViconNexusData:
         torch = self.torch
         if isinstance(data, torch.Tensor):
             if data.is_cuda:
@@ -292,6 +317,163 @@ class ViconLoader:
         return summary, ws
 
     def _run(self, src: _Source, name: str, defer_check: bool = False) -> ViconNexusData:
+        with self._lock, self.torch.cuda.device(self.device):
+            if FORCE_PATH != "two_pass" and src.n > 0:
+                if self._fused_skip > 0 and FORCE_PATH != "fused":
+                    self._fused_skip -= 1  # the last files were not for the single-pass kernel: do not run both on every one
+                else:
+                    data = self._run_fused(src, name)
+                    if data is not None:
+                        self.stats["fused"] += 1
+                        self._fused_backoff = 0
+                        return data
+            self.stats["two_pass"] += 1
+            return self._run_two_pass(src, name, defer_check)
+
+    # ---- single pass ---------------------------------------------------------------------------------
+    def _decline(self, why: str, back_off: bool = True):
+        self.stats["declined"][why] = self.stats["declined"].get(why, 0) + 1
+        if back_off:
+            self._fused_backoff = min(64, max(2, 2 * self._fused_backoff))
+            self._fused_skip = self._fused_backoff
+        return None
+
+    def _fused_sizes(self, src: _Source, name: str):
+        """(arena doubles, row capacity of each section, tile bytes) for ms_load_fused, or None.  From the previous
+        file this loader parsed when there is one (trials of one session share a layout); else from the first
+        rows of this file.  A wrong guess costs a second run (the kernel reports MS_LOAD_OVERFLOW), never a
+        wrong array."""
+        n = src.n
+        h = self._history
+        if h is not None:
+            scale = n / h["n"]
+            cap1 = int(h["rows"][0] * scale * 1.02) + 64
+            cap2 = int(h["rows"][1] * scale * 1.05) + 64
+            arena = h["keep"][0] * cap1 + 2 + h["keep"][1] * cap2
+            row_len = h["row_len"]
+        else:
+            m1 = HeaderMachine(SectionType.FORCES_EMG)
+            try:
+                err, hdr = _feed_header(src, 0, 0, 1 << 62, m1, name)
+            except Exception:  # noqa: BLE001 - the two-pass path raises it in the reference's words
+                return None
+            if err is not None or not m1.done or m1.layout.num_cols < 3:
+                return None
+            rest = src.fetch(len(hdr), _PEEK)
+            ends = [m.end() for m in _TERMINATOR.finditer(rest)]
+            if len(ends) < 2:
+                return None
+            row_len = ends[-1] / len(ends)
+            cap1 = int(n / row_len * 1.03) + 64
+            cap2 = 0  # the second section takes what is left
+            arena = (m1.layout.num_cols - 2) * cap1 + 2 + n // 12 + 4096
+        tile = nat.MS_TILE_BYTES
+        groups = int((tile + row_len / 2) // (32 * row_len))
+        if groups >= 1:
+            # just under a multiple of 32 rows per tile: the kernel parses rows in groups of 32 lanes
+            tile = max(4096, min(tile, int((32 * groups - 2) * row_len) // 16 * 16))
+        if FORCE_TILE is not None:
+            tile = int(FORCE_TILE)
+        return arena, cap1, cap2, tile
+
+    def _fmeta_acquire(self):
+        if self._fmeta_pool:
+            return self._fmeta_pool.pop()
+        torch = self.torch
+        return (torch.empty(_FMETA_BYTES, dtype=torch.uint8, device=self.device),
+                torch.empty(_FMETA_BYTES, dtype=torch.uint8, pin_memory=True))
+
+    def _run_fused(self, src: _Source, name: str) -> Optional[ViconNexusData]:
+        """ms_load_fused: bytes -> both sections' blocks in one launch.  Returns None when the kernel (or the host's
+        reading of the header text it sends back) says the file is not plain enough; the caller then runs the
+        two-pass path, which handles - and words the errors of - everything."""
+        torch = self.torch
+        sizes = self._fused_sizes(src, name)
+        if sizes is None:
+            return self._decline("no size estimate", back_off=False)
+        arena_elems, cap1, cap2, tile = sizes
+        stream, sptr = self._stream_ptr()
+        meta = self._fmeta_acquire()
+        d_meta, h_meta = meta
+        with self._on_stream(stream):
+            arena = torch.empty(arena_elems, dtype=torch.float64, device=self.device)
+            ws_bytes = int(self.lib.ms_load_workspace_bytes(src.n, tile))
+            ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
+            plan = nat.LoadPlan(arena.data_ptr(), arena_elems, (ctypes.c_int64 * 2)(cap1, cap2), tile, 0)
+            nat.check(self.lib.ms_load_fused(src.d_bytes.data_ptr(), src.n, ctypes.byref(plan), ws.data_ptr(), ws_bytes,
+                                             d_meta.data_ptr(), d_meta.data_ptr() + _FMETA_PEEK, sptr), "ms_load_fused")
+            h_meta.copy_(d_meta, non_blocking=True)
+            copied = torch.cuda.Event()
+            copied.record(stream)
+        copied.synchronize()
+        host = h_meta.numpy()
+        res = nat.LoadResult.from_buffer_copy(host[: ctypes.sizeof(nat.LoadResult)].tobytes())
+        peeks = [host[_FMETA_PEEK + s * nat.MS_LOAD_PEEK : _FMETA_PEEK + s * nat.MS_LOAD_PEEK + max(0, int(res.peek_bytes[s]))].tobytes()
+                 if res.have & (nat.MS_LOAD_HAVE_HEADER0 << s) else b"" for s in (0, 1)]
+        self._fmeta_pool.append(meta)
+        self.last_result = res
+
+        if res.flags:
+            # a wrong size guess (alone) is no reason to avoid the kernel: the two-pass run below seeds the next guess
+            return self._decline("flags " + "|".join(v for k, v in nat.MS_LOAD_FLAG_NAMES.items() if res.flags & k),
+                                 back_off=res.flags != 16)
+        if res.status != nat.MS_ERR_NONE:
+            return self._decline("bad field")
+        want = 0
+        for s in (0, 1):
+            want |= (nat.MS_LOAD_HAVE_HEADER0 | nat.MS_LOAD_HAVE_DESC0 | nat.MS_LOAD_HAVE_ROWS0) << s
+        if res.have & want != want:
+            return self._decline("not two sections")
+        if not (res.n_blank_rows == 1 or (res.n_blank_rows == 2 and res.tail_rows == 0)):
+            return self._decline("blank rows")
+        if res.data_rows[0] < 0 or res.data_rows[1] < 0:
+            return self._decline("short header")
+        layouts, header_quotes = [], 0
+        for s, kind in ((0, SectionType.FORCES_EMG), (1, SectionType.TRAJECTORIES)):
+            at_eof = int(res.header_offset[s]) + len(peeks[s]) >= src.n
+            chunk = _first_lines(peeks[s], _HEADER_LINES, at_eof)
+            if chunk is None:
+                return self._decline("header text")
+            header_quotes += chunk.count(b'"')
+            lay = _header_cache.get((chunk, kind, _HEADER_LINES))
+            if lay is None:
+                machine = HeaderMachine(kind)
+                try:
+                    rows, consumed = rows_from_bytes(chunk, _HEADER_LINES)
+                    if consumed != len(rows) or len(rows) != _HEADER_LINES:
+                        return self._decline("header text")
+                    for row in rows:
+                        machine.feed(row)
+                except Exception:  # noqa: BLE001 - raised, worded and numbered by the two-pass path
+                    return self._decline("header error")
+                lay = machine.layout
+                if lay.complete and len(_header_cache) < 64:
+                    _header_cache[(chunk, kind, _HEADER_LINES)] = lay
+            if not lay.complete or lay.num_cols != res.num_cols[s] or lay.n_keep > res.n_keep[s] or lay.num_cols < 3:
+                return self._decline("column count")
+            layouts.append(lay)
+        if int(res.n_quotes) > header_quotes:
+            return self._decline("quotes")
+
+        rows = [int(res.data_rows[0]), int(res.data_rows[1])]
+        plan_ = _Plan()
+        plan_.layouts = layouts
+        first2 = _HEADER_LINES + rows[0] + 1 + _HEADER_LINES
+        plan_.data_rows = [(_HEADER_LINES, _HEADER_LINES + rows[0]), (first2, first2 + rows[1])]
+        blocks = []
+        for s in (0, 1):
+            keep, stride, off = int(res.n_keep[s]), int(res.stride[s]), int(res.out_offset[s])
+            block = arena[off : off + keep * stride].view(keep, stride)[: layouts[s].n_keep]
+            blocks.append(SectionBlock(block, rows[s]))
+        sec1_bytes = int(res.blank_end[0]) + 1
+        self._history = {"n": src.n, "rows": rows, "keep": [int(res.n_keep[0]), int(res.n_keep[1])],
+                         "row_len": max(1.0, sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1))}
+        data = _build(plan_, blocks)  # raises what Builder.build raises (user_data.py:310-433): the rows are clean
+        data.blocks = blocks
+        return data
+
+    # ---- two passes ------------------------------------------------------------------------------------
+    def _run_two_pass(self, src: _Source, name: str, defer_check: bool = False) -> ViconNexusData:
         torch = self.torch
         summary, ws = self._scan(src)
         try:
@@ -355,7 +537,16 @@ class ViconLoader:
             data._pending_check = check
             return data
         check()
+        self._remember(src, plan)
         return data
+
+    def _remember(self, src: _Source, plan):
+        """Shapes of a file the two-pass path parsed: the single-pass kernel's size guess for the next one."""
+        lays, rows = plan.layouts, [max(0, b - a) for a, b in plan.data_rows]
+        if lays[0] is None or lays[1] is None or not (lays[0].complete and lays[1].complete) or plan.sec1_bytes <= 0:
+            return
+        self._history = {"n": src.n, "rows": rows, "keep": [lays[0].num_cols - 2, lays[1].num_cols - 2],
+                         "row_len": max(1.0, plan.sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1))}
 
     def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2, return_exceptions: bool = False):
         """Pipelined batch load: yields one ViconNexusData per source, in order.
@@ -364,8 +555,11 @@ class ViconLoader:
         non-pinned inputs are staged through a fresh pinned buffer).  While file i is scanned and
         parsed on the compute stream, file i+1 is copied host->device on a copy stream and the
         arrays of file i-1 travel device->host on a third stream (PCIe is full duplex).  With
-        to_host the section blocks are copied into a ring of `host_slots` pinned buffers: the host
-        arrays of file i stay valid until file i + host_slots is yielded.  An error in a file is
+        to_host the section blocks are copied into pinned buffers borrowed from the loader's pool: a
+        buffer belongs to the result it was filled for (its `.df` / `.host()` arrays stay valid for as
+        long as anything refers to them) and returns to the pool when the last such array is gone, so a
+        caller that lets results go recycles two or three buffers and one that keeps them all gets a
+        fresh buffer per file (`host_slots` is accepted for compatibility and ignored).  An error in a file is
         raised when that file is reached - or, with return_exceptions, yielded in its place so
         that the rest of the batch still loads."""
         torch = self.torch
@@ -377,7 +571,6 @@ class ViconLoader:
         if self._side_streams is None:
             self._side_streams = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
         s_copy, s_d2h = self._side_streams
-        ring = [dict() for _ in range(max(1, host_slots))]
         counter = [0]
 
         def stage():
@@ -427,15 +620,9 @@ class ViconLoader:
                 done = torch.cuda.Event()
                 done.record(s_comp)
                 s_d2h.wait_event(done)
-                slot = ring[i % len(ring)]
-                for bi, blk in enumerate(data.blocks):
-                    need = int(blk.tensor.shape[0]) * blk.n_rows
-                    buf = slot.get(bi)
-                    if buf is None or buf.numel() < need:
-                        buf = torch.empty(max(need, 1), dtype=torch.float64, pin_memory=True)
-                        slot[bi] = buf
+                for blk in data.blocks:
                     blk.tensor.record_stream(s_d2h)
-                    blk.prefetch_host(s_d2h, buf)
+                    blk.prefetch_host(s_d2h, pool=self._host_pool)
             yield data
             i += 1
         s_d2h.synchronize()
@@ -532,6 +719,7 @@ class _Plan:
         self.layouts: List[Optional[SectionLayout]] = [None, None]
         self.data_rows: List[Tuple[int, int]] = [(0, 0), (0, 0)]
         self.deferred_error: Optional[Exception] = None  # raised if the data rows before it are clean
+        self.sec1_bytes = 0  # bytes up to and including the blank row that closes the first section
 
 
 def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, machine: HeaderMachine, name: str):
@@ -561,6 +749,21 @@ def _feed_header(src: _Source, offset: int, first_row: int, n_rows_total: int, m
     if machine.done and len(_header_cache) < 64:
         _header_cache[(chunk, machine.expected, want)] = machine.layout
     return None, chunk
+
+
+def _first_lines(buf: bytes, k: int, at_eof: bool) -> Optional[bytes]:
+    """The first k physical lines of `buf` (which ends at the end of the file when at_eof), or None when buf
+    does not hold them completely."""
+    ends = []
+    for m in _TERMINATOR.finditer(buf):
+        if m.end() == len(buf) and buf[-1:] == b"\r" and not at_eof:
+            break  # may be half of a "\r\n"
+        ends.append(m.end())
+        if len(ends) == k:
+            return buf[: ends[-1]]
+    if at_eof and len(ends) == k - 1 and len(buf) > (ends[-1] if ends else 0):
+        return buf  # the last line is unterminated
+    return None
 
 
 class _QuotedData(Exception):
@@ -601,6 +804,7 @@ def _plan(src: _Source, summary, name: str, quoted: bool = False) -> _Plan:
     b1 = first_blank_from(_HEADER_LINES)
     end1 = b1[0] if b1 is not None else n_rows
     plan.data_rows[0] = (_HEADER_LINES, end1)
+    plan.sec1_bytes = b1[1] + 1 if b1 is not None else 0
     if b1 is None:
         _check_quotes(summary, header_quotes, quoted)
         return plan
