@@ -116,6 +116,95 @@ struct MsFusedArgs {
     long long n_tiles;
 };
 
+// ---- the field parser of the single-pass kernel ----------------------------------------------------------------
+// A field's end is known before it is read (the delimiter masks of P1), so the common shapes - an optional '-',
+// digits, at most one '.', 1 to 9 digits in all, at most 12 bytes: every number a Vicon export prints without an
+// exponent - take ONE straight-line path whatever their length, and the lanes of a warp (32 rows, same column)
+// do not diverge on digit counts:
+//   * the 12 bytes that END at the delimiter are loaded; the bytes of earlier fields in front are masked off;
+//   * chars before the '.' are moved one place towards the end (a second view of the same words, shifted by a
+//     byte), which removes the '.': the digits are then the last `ndig` chars, zero padded in front;
+//   * three 4-digit groups by integer dot products (IDP4A), one exact scaling by 10^-nfrac (ms_div_pow10_u32).
+// Everything else - exponents, blanks, '+', inf/nan, long mantissas, quotes, errors - goes to ms_parse_next.
+struct MsFieldLut {
+    uint4 last[16];     // last[n]: byte masks (three words, first char in the low byte) of the last n chars of 12
+    double2 pow10[16];  // {10^k, RN(10^-k)}
+};
+__device__ __forceinline__ void ms_field_lut_init(MsFieldLut* lut, int tid) {
+    if (tid < 16) {
+        uint32_t w[3];
+#pragma unroll
+        for (int k = 0; k < 3; k++) {
+            uint32_t m = 0;
+#pragma unroll
+            for (int b = 0; b < 4; b++)
+                if (4 * k + b >= 12 - tid) m |= 0xffu << (8 * b);
+            w[k] = m;
+        }
+        lut->last[tid] = make_uint4(w[0], w[1], w[2], 0u);
+        lut->pow10[tid] = make_double2(ms_pow10_double[tid], ms_rpow10_double[tid]);
+    }
+}
+// four chars already reduced to 0..9, first char in the low byte -> their value
+__device__ __forceinline__ uint32_t ms_digits4_dp(uint32_t g) {
+    const uint32_t hi = __dp4a(g, 0x0000010au, 0u);  // 10 c0 + c1
+    return __dp4a(g, 0x010a0000u, hi * 100u);         // + 10 c2 + c3
+}
+
+// Parses the field that starts at *pp, advances *pp past its delimiter; true when that delimiter ended the row.
+__device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, const uint16_t* __restrict__ dmask,
+                                              const MsFieldLut* __restrict__ lut, int* pp, uint64_t* bits_out,
+                                              unsigned long long* status, long long t0) {
+    const int p = *pp;
+    const int seg = p >> 4;
+    const uint32_t dm = (((uint32_t)dmask[seg + 1] << 16) | dmask[seg]) >> (p & 15);
+    const int L = __ffs(dm) - 1;  // bytes before the field's delimiter; -1: none within reach
+    const int e = p + L;
+    // the 12 bytes that end at the delimiter
+    const int a = e - 12;
+    const uint32_t* w = reinterpret_cast<const uint32_t*>(reg) + (a >> 2);
+    const int sh = (a & 3) << 3;
+    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+    const uint32_t t0w = __funnelshift_r(a0, a1, sh) ^ 0x30303030u, t1w = __funnelshift_r(a1, a2, sh) ^ 0x30303030u,
+                   t2w = __funnelshift_r(a2, a3, sh) ^ 0x30303030u;
+    const uint4 in = lut->last[L & 15];  // the chars of this field
+    // chars of the field that are not digits -> bit j of M (j = 0: 12 bytes before the delimiter)
+    const uint32_t n0 = ((t0w + 0x76767676u) | t0w) & in.x & 0x80808080u, n1 = ((t1w + 0x76767676u) | t1w) & in.y & 0x80808080u,
+                   n2 = ((t2w + 0x76767676u) | t2w) & in.z & 0x80808080u;
+    const uint32_t M = ms_gather4(n0) | (ms_gather4(n1) << 4) | (ms_gather4(n2) << 8);
+    const unsigned c0 = reg[p], ce = reg[e];
+    const uint32_t neg = c0 == '-' ? 1u : 0u;
+    const uint32_t Md = M & ~(neg << (12 - L));  // what is left must be the point
+    const int dotj = 31 - __clz(Md);              // -1: no point
+    const uint32_t hasdot = Md != 0 ? 1u : 0u;
+    const unsigned cd = reg[a + (dotj & 15)];
+    const int nfrac = hasdot ? 11 - dotj : 0;
+    const int ndig = L - (int)neg - (int)hasdot;
+    bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && (unsigned)(ndig - 1) <= 8u && (!hasdot || cd == '.');
+    // the point taken out: chars before it from the view shifted by one byte
+    const uint4 keep = lut->last[hasdot ? nfrac : 12];
+    const uint4 dig = lut->last[ndig & 15];
+    const uint32_t h0 = t0w << 8, h1 = __funnelshift_l(t0w, t1w, 8), h2 = __funnelshift_l(t1w, t2w, 8);
+    const uint32_t g0 = ((t0w & keep.x) | (h0 & ~keep.x)) & dig.x, g1 = ((t1w & keep.y) | (h1 & ~keep.y)) & dig.y,
+                   g2 = ((t2w & keep.z) | (h2 & ~keep.z)) & dig.z;
+    const uint32_t N = (ms_digits4_dp(g0) * 10000u + ms_digits4_dp(g1)) * 10000u + ms_digits4_dp(g2);
+    const double2 pw = lut->pow10[nfrac];
+    const double an = (double)N;
+    const double q0 = __dmul_rn(an, pw.y);
+    const double r = __fma_rn(-q0, pw.x, an);
+    uint64_t bits = ms_double_to_bits(__fma_rn(r, pw.y, q0)) | ((uint64_t)neg << 63);
+    if (L == 0) {  // an empty field: None -> NaN (reader.py:944-948, user_data.py:396)
+        bits = MS_NAN_BITS;
+        fast = true;
+    }
+    if (fast) {
+        *bits_out = bits;
+        *pp = e + 1;
+        return ce != ',';
+    }
+    return ms_parse_next(reg, pp, bits_out, status, t0);
+}
+
 __global__ void __launch_bounds__(FUSED_THREADS, 3)
     ms_load_kernel(const uint8_t* __restrict__ src, long long n, MsFusedWs* __restrict__ ws, const MsFusedArgs args,
                    ms_load_result* __restrict__ res, uint8_t* __restrict__ peek) {
@@ -132,10 +221,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
     __shared__ int s_q, s_commas;
     __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
     __shared__ __align__(8) unsigned long long s_stage_bar;
+    __shared__ __align__(16) MsFieldLut s_lut;
+    __shared__ uint32_t s_inv_groups;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* const lb = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + FUSED_LB_OFFSET);
 
+    ms_field_lut_init(&s_lut, tid);
     if (tid == 0) {
         s_tile = atomicAdd(&ws->ticket, 1u);
         s_lt_end = -1;
@@ -272,6 +364,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
             if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
             const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
             tmask[v] = (uint16_t)term;
+            cmask[v] |= (uint16_t)(lf | cr);  // a field also ends at a line end: commas + line-end bytes = delimiters
             my_terms += __popc(term);
             if (mine) {
                 const int p0 = v << 4;
@@ -293,12 +386,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
     if (my_quotes) atomicAdd(&s_quotes, my_quotes);
     if (my_flags) atomicOr(&s_flags, my_flags);
     __syncthreads();
-    int before = 0, total_terms = 0;
+    int before, total_terms;
+    {
+        const int mine_w = lane < FUSED_WARPS ? s_warp_terms[lane] : 0;
+        int sc = mine_w;
 #pragma unroll
-    for (int w = 0; w < FUSED_WARPS; w++) {
-        const int c = s_warp_terms[w];
-        if (w < warp) before += c;
-        total_terms += c;
+        for (int d = 1; d < FUSED_WARPS; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, sc, d);
+            if (lane >= d) sc += o;
+        }
+        total_terms = __shfl_sync(0xffffffffu, sc, FUSED_WARPS - 1);
+        before = __shfl_sync(0xffffffffu, sc - mine_w, warp);
     }
     const int lt0 = before + inc - my_terms;  // terminators before my segments
     if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
@@ -551,6 +649,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
         if (tabulated && tid <= PARSE_MAX_CHUNKS) s_chunk_col[tid] = __ldcg(&desc->chunk_tab[groups - 1][tid]);
         if (tid == 0) {
             s_next_item = 0;
+            s_inv_groups = (65536u + groups - 1) / groups;  // item / groups by multiply-shift (items < 2^10)
             if (tabulated)
                 s_nchunks = __ldcg(&desc->chunk_cnt[groups - 1]);
             else
@@ -561,7 +660,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
         // lanes = rows, in lockstep over the columns of a chunk; warps draw (row group, column chunk) items
         const int nchunks = s_nchunks;
         const int items = groups * nchunks;
-        const uint32_t inv_groups = (65536u + groups - 1) / groups;  // item / groups by multiply-shift (items < 2^10)
+        const uint32_t inv_groups = s_inv_groups;
         unsigned long long* const status = reinterpret_cast<unsigned long long*>(&res->status);
         for (;;) {
             int item = 0;
@@ -597,7 +696,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
                 double* out = out_base + (long long)(c_lo - 2) * out_stride + (out_row0 + r);
                 for (int c = c_lo; c < c_hi; c++, out += out_stride) {
                     uint64_t bits = MS_NAN_BITS;
-                    if (!done) done = ms_parse_next(reg, &p, &bits, status, t0);
+                    if (!done) done = ms_field_next(reg, cmask, &s_lut, &p, &bits, status, t0);
                     const int ch = c - 2;
                     if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
                 }

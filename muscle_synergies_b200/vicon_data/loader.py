@@ -60,6 +60,7 @@ _read_pool = None
 # FORCE_TILE: CSV bytes per thread block of the single-pass kernel (tests sweep it to move tile boundaries).
 FORCE_PATH = os.environ.get("MS_B200_LOADER") or None
 FORCE_TILE = None
+TUNE_TILE = os.environ.get("MS_B200_TUNE_TILE") == "1"  # size tiles to just under a multiple of 32 rows
 _FMETA_PEEK = 256  # offset of the two header peeks behind ms_load_result in the single-pass meta buffer
 _FMETA_BYTES = _FMETA_PEEK + 2 * nat.MS_LOAD_PEEK
 
@@ -369,7 +370,7 @@ class ViconLoader:
             arena = (m1.layout.num_cols - 2) * cap1 + 2 + n // 12 + 4096
         tile = nat.MS_TILE_BYTES
         groups = int((tile + row_len / 2) // (32 * row_len))
-        if groups >= 1:
+        if groups >= 1 and TUNE_TILE:
             # just under a multiple of 32 rows per tile: the kernel parses rows in groups of 32 lanes
             tile = max(4096, min(tile, int((32 * groups - 2) * row_len) // 16 * 16))
         if FORCE_TILE is not None:
