@@ -29,8 +29,8 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 // the end of every tile).  The widest chunk is the END of the row: in a Devices row those are the EMG
 // columns, the longest fields.  cols[] is descending: chunk j covers columns [cols[j+1], cols[j]).
 template <typename T>
-__host__ __device__ inline int ms_chunk_table(int groups, int ncols, T* cols) {
-    const int ideal = (groups * ncols + PARSE_WARPS - 1) / PARSE_WARPS;  // column-groups per warp
+__host__ __device__ inline int ms_chunk_table(int groups, int ncols, T* cols, int warps = PARSE_WARPS) {
+    const int ideal = (groups * ncols + warps - 1) / warps;  // column-groups per warp
     int u = (ideal * MS_EXP_UNUM + MS_EXP_UDEN - 1) / MS_EXP_UDEN;
     if (u < 2) u = 2;
     int k = 0, col = 0;

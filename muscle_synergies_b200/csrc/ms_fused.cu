@@ -23,9 +23,16 @@
 
 #include "ms_field.cuh"
 
-#define FUSED_THREADS PARSE_THREADS
+#ifndef FUSED_THREADS
+#define FUSED_THREADS 512
+#endif
 #define FUSED_WARPS (FUSED_THREADS / 32)
-#define FUSED_MAX_TILE MS_TILE_BYTES
+#ifndef FUSED_MAX_TILE
+#define FUSED_MAX_TILE MS_TILE_BYTES  // largest tile (and the default)
+#endif
+#ifndef FUSED_MIN_CTAS
+#define FUSED_MIN_CTAS 3
+#endif
 #define FUSED_MAX_REGION (FUSED_MAX_TILE + MS_MAX_ROW_BYTES)
 #define FUSED_MAX_NSEG (FUSED_MAX_REGION / 16)
 #define FUSED_PAD 16
@@ -37,10 +44,12 @@
 #define FUSED_OFF_TMASK (FUSED_OFF_CMASK + FUSED_MAX_NSEG * 2 + 16)
 #define FUSED_OFF_HIT (FUSED_OFF_TMASK + FUSED_MAX_NSEG * 2)
 #define FUSED_OFF_ROWS (FUSED_OFF_HIT + FUSED_HIT_WORDS * 4)
-#define FUSED_SMEM (FUSED_OFF_ROWS + (FUSED_ROWS_CAP + 2) * 2 + 12)
+#define FUSED_OFF_LUT ((FUSED_OFF_ROWS + (FUSED_ROWS_CAP + 2) * 2 + 15) / 16 * 16)
+#define FUSED_SMEM (FUSED_OFF_LUT + 512)
 static_assert(FUSED_OFF_CMASK % 16 == 0 && FUSED_OFF_TMASK % 16 == 0 && FUSED_OFF_HIT % 8 == 0 && FUSED_OFF_ROWS % 4 == 0,
               "shared memory layout");
 static_assert(FUSED_MAX_REGION + FUSED_PAD < 65536, "row starts are 16-bit");
+static_assert(sizeof(double2) * 16 + sizeof(uint4) * 16 == 512, "MsFieldLut is 512 bytes");
 
 // ---- workspace: everything the tiles tell each other (zeroed before the launch) -----------------------------
 struct MsSecDesc {
@@ -151,44 +160,74 @@ __device__ __forceinline__ uint32_t ms_digits4_dp(uint32_t g) {
     return __dp4a(g, 0x010a0000u, hi * 100u);         // + 10 c2 + c3
 }
 
+// Shared-memory loads by 32-bit shared-window address: one base register for the whole loop instead of a generic
+// pointer that is converted again at every use.  volatile: they stay ordered with the barriers around them.
+__device__ __forceinline__ uint32_t lds_u8(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u16(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u16 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint4 lds_v4(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ double2 lds_d2(uint32_t a) {
+    double2 v;
+    asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(a));
+    return v;
+}
+
 // Parses the field that starts at *pp, advances *pp past its delimiter; true when that delimiter ended the row.
-__device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, const uint16_t* __restrict__ dmask,
-                                              const MsFieldLut* __restrict__ lut, int* pp, uint64_t* bits_out,
-                                              unsigned long long* status, long long t0) {
+// sreg / sdm / slut: shared-window addresses of reg[0], the delimiter masks and the MsFieldLut.
+__device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, uint32_t sreg, uint32_t sdm, uint32_t slut,
+                                              int* pp, uint64_t* bits_out, unsigned long long* status, long long t0) {
     const int p = *pp;
-    const int seg = p >> 4;
-    const uint32_t dm = (((uint32_t)dmask[seg + 1] << 16) | dmask[seg]) >> (p & 15);
+    const uint32_t sd = sdm + ((p >> 4) << 1);
+    const uint32_t dm = ((lds_u16(sd + 2) << 16) | lds_u16(sd)) >> (p & 15);
     const int L = __ffs(dm) - 1;  // bytes before the field's delimiter; -1: none within reach
     const int e = p + L;
     // the 12 bytes that end at the delimiter
     const int a = e - 12;
-    const uint32_t* w = reinterpret_cast<const uint32_t*>(reg) + (a >> 2);
+    const uint32_t sw = sreg + (a & ~3);
     const int sh = (a & 3) << 3;
-    const uint32_t a0 = w[0], a1 = w[1], a2 = w[2], a3 = w[3];
+    const uint32_t a0 = lds_u32(sw), a1 = lds_u32(sw + 4), a2 = lds_u32(sw + 8), a3 = lds_u32(sw + 12);
     const uint32_t t0w = __funnelshift_r(a0, a1, sh) ^ 0x30303030u, t1w = __funnelshift_r(a1, a2, sh) ^ 0x30303030u,
                    t2w = __funnelshift_r(a2, a3, sh) ^ 0x30303030u;
-    const uint4 in = lut->last[L & 15];  // the chars of this field
+    const uint4 in = lds_v4(slut + ((L & 15) << 4));  // the chars of this field
     // chars of the field that are not digits -> bit j of M (j = 0: 12 bytes before the delimiter)
     const uint32_t n0 = ((t0w + 0x76767676u) | t0w) & in.x & 0x80808080u, n1 = ((t1w + 0x76767676u) | t1w) & in.y & 0x80808080u,
                    n2 = ((t2w + 0x76767676u) | t2w) & in.z & 0x80808080u;
     const uint32_t M = ms_gather4(n0) | (ms_gather4(n1) << 4) | (ms_gather4(n2) << 8);
-    const unsigned c0 = reg[p], ce = reg[e];
+    const unsigned c0 = lds_u8(sreg + p), ce = lds_u8(sreg + e);
     const uint32_t neg = c0 == '-' ? 1u : 0u;
     const uint32_t Md = M & ~(neg << (12 - L));  // what is left must be the point
     const int dotj = 31 - __clz(Md);              // -1: no point
     const uint32_t hasdot = Md != 0 ? 1u : 0u;
-    const unsigned cd = reg[a + (dotj & 15)];
+    const unsigned cd = lds_u8(sreg + a + (dotj & 15));
     const int nfrac = hasdot ? 11 - dotj : 0;
     const int ndig = L - (int)neg - (int)hasdot;
-    bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && (unsigned)(ndig - 1) <= 8u && (!hasdot || cd == '.');
     // the point taken out: chars before it from the view shifted by one byte
-    const uint4 keep = lut->last[hasdot ? nfrac : 12];
-    const uint4 dig = lut->last[ndig & 15];
+    const uint4 keep = lds_v4(slut + ((hasdot ? nfrac : 12) << 4));
+    const uint4 dig = lds_v4(slut + ((ndig & 15) << 4));
     const uint32_t h0 = t0w << 8, h1 = __funnelshift_l(t0w, t1w, 8), h2 = __funnelshift_l(t1w, t2w, 8);
     const uint32_t g0 = ((t0w & keep.x) | (h0 & ~keep.x)) & dig.x, g1 = ((t1w & keep.y) | (h1 & ~keep.y)) & dig.y,
                    g2 = ((t2w & keep.z) | (h2 & ~keep.z)) & dig.z;
-    const uint32_t N = (ms_digits4_dp(g0) * 10000u + ms_digits4_dp(g1)) * 10000u + ms_digits4_dp(g2);
-    const double2 pw = lut->pow10[nfrac];
+    const uint32_t v0 = ms_digits4_dp(g0);
+    const uint32_t N = (v0 * 10000u + ms_digits4_dp(g1)) * 10000u + ms_digits4_dp(g2);
+    // 1 to 12 digits whose value fits 32 bits (leading zeros are free: "-0.000944047" has ten digits)
+    bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && ndig >= 1 && v0 <= 41u && (!hasdot || cd == '.');
+    const double2 pw = lds_d2(slut + 256 + (nfrac << 4));
     const double an = (double)N;
     const double q0 = __dmul_rn(an, pw.y);
     const double r = __fma_rn(-q0, pw.x, an);
@@ -205,7 +244,7 @@ __device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, c
     return ms_parse_next(reg, pp, bits_out, status, t0);
 }
 
-__global__ void __launch_bounds__(FUSED_THREADS, 3)
+__global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     ms_load_kernel(const uint8_t* __restrict__ src, long long n, MsFusedWs* __restrict__ ws, const MsFusedArgs args,
                    ms_load_result* __restrict__ res, uint8_t* __restrict__ peek) {
     extern __shared__ __align__(16) uint8_t smem_raw[];
@@ -221,14 +260,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
     __shared__ int s_q, s_commas;
     __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
     __shared__ __align__(8) unsigned long long s_stage_bar;
-    __shared__ __align__(16) MsFieldLut s_lut;
+    MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + FUSED_OFF_LUT);
     __shared__ uint32_t s_inv_groups;
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* const lb = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + FUSED_LB_OFFSET);
 
-    ms_field_lut_init(&s_lut, tid);
+    ms_field_lut_init(lut_p, tid);
     if (tid == 0) {
+        // Which tile this block gets is decided by a ticket (below), one L2 round trip away.  Meanwhile ask L2 for the
+        // tile its block index names: tickets only permute tiles among blocks that start together, so this is the
+        // tile some block is about to stage.
+        const long long pf0 = (long long)blockIdx.x * args.tile_bytes;
+        const long long pfb = min((long long)args.region_bytes, n - pf0) & ~15ll;
+        if (pfb > 0)
+            asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;\n" ::"l"(src + pf0), "r"((uint32_t)pfb) : "memory");
         s_tile = atomicAdd(&ws->ticket, 1u);
         s_lt_end = -1;
         s_nblank = 0;
@@ -310,23 +356,19 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
         }
     }
 
-    // ---- P1a. every 16-byte segment once, lanes on consecutive segments: comma mask (exact) and a quick test for
-    // "some byte is below 0x23 or above 0x7f" - line ends, quotes, blanks, control and non-ASCII bytes; a data row has
-    // one or two such segments, the rest is digits, signs, points and commas.  (w - 0x23..) | w has bit 7 of a byte set
-    // for every such byte; a borrow can only add a false hit on a '#' that follows one.
+    // ---- P1a. every 16-byte segment once, lanes on consecutive segments: a quick test for "some byte is below 0x23
+    // or above 0x7f" - line ends, quotes, blanks, control and non-ASCII bytes; a data row has one or two such
+    // segments, the rest is digits, signs, points and commas.  (w - 0x23..) | w has bit 7 of a byte set for every such
+    // byte; a borrow can only add a false hit on a '#' that follows one.  (The comma masks wait until this tile has
+    // told the others what it holds: they are computed in the shadow of the look-back, P3.)
     for (int base = 0; base < nseg; base += FUSED_THREADS) {
         const int v = base + tid;
         const bool in = v < nseg;
-        uint32_t ctrl = 0, cm = 0;
+        uint32_t ctrl = 0;
         if (in) {
             const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
-            const uint32_t w[4] = {x.x, x.y, x.z, x.w};
-#pragma unroll
-            for (int k = 0; k < 4; k++) {
-                ctrl |= (w[k] - 0x23232323u) | w[k];
-                cm |= ms_gather4(ms_eq_flags(w[k], 0x2c2c2c2cu)) << (4 * k);
-            }
-            cmask[v] = (uint16_t)cm;
+            ctrl = ((x.x - 0x23232323u) | x.x) | ((x.y - 0x23232323u) | x.y) | ((x.z - 0x23232323u) | x.z) |
+                   ((x.w - 0x23232323u) | x.w);
         }
         const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
         if (lane == 0 && v < nseg) hitmap[v >> 5] = hits;
@@ -364,7 +406,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
             if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
             const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
             tmask[v] = (uint16_t)term;
-            cmask[v] |= (uint16_t)(lf | cr);  // a field also ends at a line end: commas + line-end bytes = delimiters
+            cmask[v] = (uint16_t)(lf | cr);  // a field also ends at a line end; the commas join in P3
             my_terms += __popc(term);
             if (mine) {
                 const int p0 = v << 4;
@@ -513,6 +555,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
             }
         }
     }
+    else {
+        // the other warps meanwhile: delimiter mask of every segment = its commas (exact) + the line-end bytes P1b left
+        for (int v = tid - 32; v < nseg; v += FUSED_THREADS - 32) {
+            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+            uint32_t cm = ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu), ms_eq_flags(x.z, 0x2c2c2c2cu),
+                                    ms_eq_flags(x.w, 0x2c2c2c2cu));
+            if ((hitmap[v >> 5] >> (v & 31)) & 1u) cm |= cmask[v];
+            cmask[v] = (uint16_t)cm;
+        }
+    }
     if (tid == 0) {
         if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
         const uint32_t f = s_flags | fatal | (nb > 2 ? MS_LOAD_MANY_BLANKS : 0u);
@@ -578,7 +630,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
             const int ncols = last >= 0 ? s_commas + 1 : 0;
             const int keep = ncols - 2;
             if (tid < PARSE_TAB_GROUPS && ncols > 0 && ncols <= 65535)
-                desc->chunk_cnt[tid] = (uint8_t)ms_chunk_table(tid + 1, ncols, desc->chunk_tab[tid]);
+                desc->chunk_cnt[tid] = (uint8_t)ms_chunk_table(tid + 1, ncols, desc->chunk_tab[tid], FUSED_WARPS);
             __syncthreads();
             if (tid == 0) {
                 long long offset = 0, stride = args.cap_rows[sec];
@@ -653,7 +705,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
             if (tabulated)
                 s_nchunks = __ldcg(&desc->chunk_cnt[groups - 1]);
             else
-                s_nchunks = ms_chunk_table(groups, ncols, s_chunk_col);
+                s_nchunks = ms_chunk_table(groups, ncols, s_chunk_col, FUSED_WARPS);
         }
         __syncthreads();
 
@@ -661,6 +713,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
         const int nchunks = s_nchunks;
         const int items = groups * nchunks;
         const uint32_t inv_groups = s_inv_groups;
+        // one register holds the shared-window address of the staged bytes for the whole loop (a plain value would
+        // be recomputed from the special registers at every use under this kernel's register budget)
+        uint32_t sreg = (uint32_t)__cvta_generic_to_shared(reg);
+#ifndef FUSED_NO_PIN
+        asm volatile("mov.u32 %0, %0;" : "+r"(sreg));
+#endif
+        const uint32_t sdm = sreg + (FUSED_OFF_CMASK - FUSED_PAD), slut = sreg + (FUSED_OFF_LUT - FUSED_PAD);
         unsigned long long* const status = reinterpret_cast<unsigned long long*>(&res->status);
         for (;;) {
             int item = 0;
@@ -696,7 +755,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, 3)
                 double* out = out_base + (long long)(c_lo - 2) * out_stride + (out_row0 + r);
                 for (int c = c_lo; c < c_hi; c++, out += out_stride) {
                     uint64_t bits = MS_NAN_BITS;
-                    if (!done) done = ms_field_next(reg, cmask, &s_lut, &p, &bits, status, t0);
+                    if (!done) done = ms_field_next(reg, sreg, sdm, slut, &p, &bits, status, t0);
                     const int ch = c - 2;
                     if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
                 }
