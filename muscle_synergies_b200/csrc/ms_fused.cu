@@ -107,6 +107,16 @@ __device__ __forceinline__ unsigned long long ld_acquire_u64(const unsigned long
 __device__ __forceinline__ void st_release_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.release.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
+__device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.gpu.global.u64 %0, [%1];\n" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
+}
+// barrier among the worker warps only (warp 0 is away looking back)
+__device__ __forceinline__ void ms_bar_workers(int n) { asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -255,7 +265,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     uint16_t* const row_start = reinterpret_cast<uint16_t*>(smem_raw + FUSED_OFF_ROWS);  // [L]: first byte of local row L
     __shared__ int s_warp_terms[FUSED_WARPS];
     __shared__ int s_lt_end, s_next_item, s_nchunks, s_nblank, s_blank_lo, s_blank_hi, s_quotes, s_stop;
-    __shared__ uint32_t s_tile, s_flags, s_pre_nb;
+    __shared__ uint32_t s_tile, s_flags, s_pre_nb, s_agg_nb, s_fatal;
+    __shared__ unsigned long long s_agg_dist;
+    __shared__ int s_agg_ready;
     __shared__ unsigned long long s_pre_dist;
     __shared__ int s_q, s_commas;
     __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
@@ -283,6 +295,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         s_quotes = 0;
         s_flags = 0;
         s_stop = 0;
+        s_agg_ready = 0;
+        s_fatal = 0;
     }
     __syncthreads();
     const long long tile = (long long)s_tile;
@@ -342,185 +356,34 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     }
     if (tid < 2) hitmap[(nseg >> 5) + tid] = 0;  // the words a thread's hit window may reach past the last segment
     __syncthreads();  // mbarrier init and the hand-filled chunks are visible
-    {
-        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
-        uint32_t done = 0;
-        while (!done) {
-            asm volatile(
-                "{\n.reg .pred p;\n"
-                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
-                "selp.u32 %0, 1, 0, p;\n}\n"
-                : "=r"(done)
-                : "r"(bar)
-                : "memory");
-        }
-    }
 
-    // ---- P1a. every 16-byte segment once, lanes on consecutive segments: a quick test for "some byte is below 0x23
-    // or above 0x7f" - line ends, quotes, blanks, control and non-ASCII bytes; a data row has one or two such
-    // segments, the rest is digits, signs, points and commas.  (w - 0x23..) | w has bit 7 of a byte set for every such
-    // byte; a borrow can only add a false hit on a '#' that follows one.  (The comma masks wait until this tile has
-    // told the others what it holds: they are computed in the shadow of the look-back, P3.)
-    for (int base = 0; base < nseg; base += FUSED_THREADS) {
-        const int v = base + tid;
-        const bool in = v < nseg;
-        uint32_t ctrl = 0;
-        if (in) {
-            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
-            ctrl = ((x.x - 0x23232323u) | x.x) | ((x.y - 0x23232323u) | x.y) | ((x.z - 0x23232323u) | x.z) |
-                   ((x.w - 0x23232323u) | x.w);
-        }
-        const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
-        if (lane == 0 && v < nseg) hitmap[v >> 5] = hits;
-    }
-    __syncthreads();
-
-    // ---- P1b. a thread owns a run of consecutive segments; the exact line ends of those the quick test hit
-    // (universal newlines: '\n', "\r\n", lone '\r' - what open(filename) gives csv.reader, load_csv.py:29)
-    const int vpt = (nseg + FUSED_THREADS - 1) / FUSED_THREADS;  // segments per thread, <= 7
-    const int v0 = tid * vpt;
-    uint32_t my_hits = 0;
-    if (v0 < nseg) {
-        const uint32_t h0 = hitmap[v0 >> 5], h1 = hitmap[(v0 >> 5) + 1];
-        my_hits = __funnelshift_r(h0, h1, v0 & 31) & ((1u << vpt) - 1u);
-    }
-    int my_terms = 0, my_quotes = 0;
-    uint32_t my_flags = 0;
-    int lt_end_part = -1;  // terminators of my segments before position tile_len - 1, if that position is mine
-    {
-        const int q = tile_len - 1;
-        const bool mine = q >= (v0 << 4) && q < ((v0 + vpt) << 4);
-        if (mine) lt_end_part = 0;
-        uint32_t hb = my_hits;
-        while (hb) {
-            const int k = __ffs(hb) - 1;
-            hb &= hb - 1u;
-            const int v = v0 + k;
-            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
-            const uint32_t lf = ms_mask16(ms_eq_flags(x.x, 0x0a0a0a0au), ms_eq_flags(x.y, 0x0a0a0a0au),
-                                          ms_eq_flags(x.z, 0x0a0a0a0au), ms_eq_flags(x.w, 0x0a0a0a0au));
-            const uint32_t cr = ms_mask16(ms_eq_flags(x.x, 0x0d0d0d0du), ms_eq_flags(x.y, 0x0d0d0d0du),
-                                          ms_eq_flags(x.z, 0x0d0d0d0du), ms_eq_flags(x.w, 0x0d0d0d0du));
-            my_quotes += __popc(ms_eq_flags(x.x, 0x22222222u)) + __popc(ms_eq_flags(x.y, 0x22222222u)) +
-                         __popc(ms_eq_flags(x.z, 0x22222222u)) + __popc(ms_eq_flags(x.w, 0x22222222u));
-            if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
-            const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
-            tmask[v] = (uint16_t)term;
-            cmask[v] = (uint16_t)(lf | cr);  // a field also ends at a line end; the commas join in P3
-            my_terms += __popc(term);
-            if (mine) {
-                const int p0 = v << 4;
-                if (q >= p0 + 16)
-                    lt_end_part += __popc(term);
-                else if (q > p0)
-                    lt_end_part += __popc(term & ((1u << (q - p0)) - 1u));
-            }
-        }
-    }
-    // block-wide exclusive prefix sum of the terminator counts
-    int inc = my_terms;
-#pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        const int o = __shfl_up_sync(0xffffffffu, inc, d);
-        if (lane >= d) inc += o;
-    }
-    if (lane == 31) s_warp_terms[warp] = inc;
-    if (my_quotes) atomicAdd(&s_quotes, my_quotes);
-    if (my_flags) atomicOr(&s_flags, my_flags);
-    __syncthreads();
-    int before, total_terms;
-    {
-        const int mine_w = lane < FUSED_WARPS ? s_warp_terms[lane] : 0;
-        int sc = mine_w;
-#pragma unroll
-        for (int d = 1; d < FUSED_WARPS; d <<= 1) {
-            const int o = __shfl_up_sync(0xffffffffu, sc, d);
-            if (lane >= d) sc += o;
-        }
-        total_terms = __shfl_sync(0xffffffffu, sc, FUSED_WARPS - 1);
-        before = __shfl_sync(0xffffffffu, sc - mine_w, warp);
-    }
-    const int lt0 = before + inc - my_terms;  // terminators before my segments
-    if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
-    // local row L starts right after the L-th terminator of the region (L >= 1); row 0 starts at byte 0
-    {
-        int lt = lt0;
-        uint32_t hb = my_hits;
-        while (hb) {
-            const int k = __ffs(hb) - 1;
-            hb &= hb - 1u;
-            const int v = v0 + k;
-            uint32_t term = tmask[v];
-            while (term) {
-                const int b = __ffs(term) - 1;
-                term &= term - 1u;
-                lt++;
-                if (lt <= FUSED_ROWS_CAP + 1) row_start[lt] = (uint16_t)((v << 4) + b + 1);
-            }
-        }
-        if (tid == 0) row_start[0] = 0;
-    }
-    __syncthreads();
-
-    // ---- ownership: the rows that START in [t0, t0 + tile_len)
-    const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
-    const int lt_first = starts_at_t0 ? 0 : 1;
-    const int lt_last = s_lt_end;  // inclusive; tile_len >= 1, so some thread set it
-    int n_own = lt_last - lt_first + 1;
-    if (n_own < 0) n_own = 0;
-    uint32_t fatal = 0;  // conditions under which this tile cannot tell its rows apart
-    if (n_own > 0 && total_terms < lt_last + 1) fatal |= MS_LOAD_ROW_TOO_LONG;  // the last owned row does not end in the region
-    if (lt_last + 1 > FUSED_ROWS_CAP) fatal |= MS_LOAD_DENSE_ROWS;
-
-    // ---- P2. blank rows (section separators): every field empty after str.strip() (reader.py:886-901).  A data
-    // row starts with its frame number, so only rows that start with a comma or a blank are looked at in full.
-    if (!fatal) {
-        for (int L = lt_first + tid; L <= lt_last; L += FUSED_THREADS) {
-            const int p = row_start[L], e = row_start[L + 1];
-            const unsigned c = reg[p];
-            if (c == ',' || c <= 0x20u) {
-                bool blank = true;
-                for (int i = p; i < e; i++) {
-                    const unsigned b = reg[i];
-                    if (!(b == ',' || ms_is_strip_space(b))) {
-                        blank = false;
-                        break;
-                    }
-                }
-                if (blank) {
-                    atomicAdd(&s_nblank, 1);
-                    atomicMin(&s_blank_lo, L);
-                    atomicMax(&s_blank_hi, L);
-                }
-            }
-        }
-    }
-    __syncthreads();
-    const int nb = s_nblank;
-    const int blank_lo = s_blank_lo, blank_hi = s_blank_hi;
-
-    // ---- P3. publish what this tile adds, look back for what came before it
+    // From here to P4 the block works in two parts.  Warp 0 looks back: what it needs - the words of the tiles before
+    // this one - does not depend on this tile's bytes, so it starts at once and its L2 round trips run under the
+    // staging and P1/P2 of the other warps instead of after them (measured: a third of a block's lifetime went by
+    // with all sixteen warps parked behind the look-back).  Warps 1.. (the "workers", synchronised among themselves
+    // on named barrier 1) find this tile's rows and publish its aggregate as soon as it is known.
+    constexpr int NW = FUSED_THREADS - 32, WW = FUSED_WARPS - 1;
+    const int wtid = tid - 32;
+    const int nseg_ = nseg;
+    int lt_first = 0, lt_last = -1, n_own = 0, nb = 0, blank_lo = 0, blank_hi = -1;
+    uint32_t fatal = 0;
     if (warp == 0) {
-        LbVal agg;
-        agg.nb = (uint32_t)min(nb, 3);
-        agg.dist = (unsigned long long)(nb ? lt_last - blank_hi : n_own);
         LbVal pre;
         pre.nb = 0;
         pre.dist = 0;
         if (tile > 0) {
-            if (lane == 0) st_release_u64(&lb[tile], lb_pack(LB_AGGREGATE, agg));
             long long j = tile - 1;
             for (;;) {
                 const long long idx = j - lane;
                 unsigned long long w = LB_INCLUSIVE << 62;  // before the first tile: nothing (no blank rows, no rows)
-                if (idx >= 0) w = ld_acquire_u64(&lb[idx]);
+                if (idx >= 0) w = ld_relaxed_u64(&lb[idx]);
                 const uint32_t state = (uint32_t)(w >> 62);
                 const uint32_t invalid = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INVALID);
                 const uint32_t inclusive = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INCLUSIVE);
                 const int count = inclusive ? __ffs(inclusive) : 32;  // lanes 0 .. count-1 are what is needed
                 const uint32_t need = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
                 if (invalid & need) {
-                    __nanosleep(40);
+                    __nanosleep(100);
                     continue;
                 }
                 LbVal val = lb_unpack(w);
@@ -536,12 +399,16 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 if (inclusive) break;
                 j -= 32;
             }
-            pre.nb = __shfl_sync(0xffffffffu, pre.nb, 0);
-            pre.dist = __shfl_sync(0xffffffffu, pre.dist, 0);
         }
         if (lane == 0) {
+            // this tile's own share comes from the workers (shared memory)
+            while (*(volatile int*)&s_agg_ready == 0) __nanosleep(20);
+            __threadfence_block();
+            LbVal agg;
+            agg.nb = *(volatile uint32_t*)&s_agg_nb;
+            agg.dist = *(volatile unsigned long long*)&s_agg_dist;
             const LbVal incl = lb_combine(pre, agg);
-            st_release_u64(&lb[tile], lb_pack(LB_INCLUSIVE, incl));
+            st_relaxed_u64(&lb[tile], lb_pack(LB_INCLUSIVE, incl));
             s_pre_nb = pre.nb;
             s_pre_dist = pre.dist;
             if (tile == args.n_tiles - 1) {
@@ -554,10 +421,189 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 }
             }
         }
-    }
-    else {
-        // the other warps meanwhile: delimiter mask of every segment = its commas (exact) + the line-end bytes P1b left
-        for (int v = tid - 32; v < nseg; v += FUSED_THREADS - 32) {
+        {
+            // the staged bytes are read by this warp too from P4 on: observe the bulk copy's completion (long done)
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n.reg .pred p;\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                    "selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done)
+                    : "r"(bar)
+                    : "memory");
+            }
+        }
+    } else {
+        {
+            const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+            uint32_t done = 0;
+            while (!done) {
+                asm volatile(
+                    "{\n.reg .pred p;\n"
+                    "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                    "selp.u32 %0, 1, 0, p;\n}\n"
+                    : "=r"(done)
+                    : "r"(bar)
+                    : "memory");
+            }
+        }
+        // ---- P1a. every 16-byte segment once, lanes on consecutive segments: a quick test for "some byte is below
+        // 0x23 or above 0x7f" - line ends, quotes, blanks, control and non-ASCII bytes; a data row has one or two such
+        // segments, the rest is digits, signs, points and commas.  (w - 0x23..) | w has bit 7 of a byte set for every
+        // such byte; a borrow can only add a false hit on a '#' that follows one.
+        for (int base = 0; base < nseg_; base += NW) {
+            const int v = base + wtid;
+            const bool in = v < nseg_;
+            uint32_t ctrl = 0;
+            if (in) {
+                const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+                ctrl = ((x.x - 0x23232323u) | x.x) | ((x.y - 0x23232323u) | x.y) | ((x.z - 0x23232323u) | x.z) |
+                       ((x.w - 0x23232323u) | x.w);
+            }
+            const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
+            if (lane == 0 && v < nseg_) hitmap[v >> 5] = hits;
+        }
+        ms_bar_workers(NW);
+
+        // ---- P1b. a worker owns a run of consecutive segments; the exact line ends of those the quick test hit
+        // (universal newlines: '\n', "\r\n", lone '\r' - what open(filename) gives csv.reader, load_csv.py:29)
+        const int vpt = (nseg_ + NW - 1) / NW;  // segments per worker, <= 8
+        const int v0 = wtid * vpt;
+        uint32_t my_hits = 0;
+        if (v0 < nseg_) {
+            const uint32_t h0 = hitmap[v0 >> 5], h1 = hitmap[(v0 >> 5) + 1];
+            my_hits = __funnelshift_r(h0, h1, v0 & 31) & ((1u << vpt) - 1u);
+        }
+        int my_terms = 0, my_quotes = 0;
+        uint32_t my_flags = 0;
+        int lt_end_part = -1;  // terminators of my segments before position tile_len - 1, if that position is mine
+        {
+            const int q = tile_len - 1;
+            const bool mine = q >= (v0 << 4) && q < ((v0 + vpt) << 4);
+            if (mine) lt_end_part = 0;
+            uint32_t hb = my_hits;
+            while (hb) {
+                const int k = __ffs(hb) - 1;
+                hb &= hb - 1u;
+                const int v = v0 + k;
+                const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+                const uint32_t lf = ms_mask16(ms_eq_flags(x.x, 0x0a0a0a0au), ms_eq_flags(x.y, 0x0a0a0a0au),
+                                              ms_eq_flags(x.z, 0x0a0a0a0au), ms_eq_flags(x.w, 0x0a0a0a0au));
+                const uint32_t cr = ms_mask16(ms_eq_flags(x.x, 0x0d0d0d0du), ms_eq_flags(x.y, 0x0d0d0d0du),
+                                              ms_eq_flags(x.z, 0x0d0d0d0du), ms_eq_flags(x.w, 0x0d0d0d0du));
+                my_quotes += __popc(ms_eq_flags(x.x, 0x22222222u)) + __popc(ms_eq_flags(x.y, 0x22222222u)) +
+                             __popc(ms_eq_flags(x.z, 0x22222222u)) + __popc(ms_eq_flags(x.w, 0x22222222u));
+                if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
+                const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
+                tmask[v] = (uint16_t)term;
+                cmask[v] = (uint16_t)(lf | cr);  // a field also ends at a line end; the commas join below
+                my_terms += __popc(term);
+                if (mine) {
+                    const int p0 = v << 4;
+                    if (q >= p0 + 16)
+                        lt_end_part += __popc(term);
+                    else if (q > p0)
+                        lt_end_part += __popc(term & ((1u << (q - p0)) - 1u));
+                }
+            }
+        }
+        // exclusive prefix sum of the terminator counts over the workers
+        int inc = my_terms;
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const int o = __shfl_up_sync(0xffffffffu, inc, d);
+            if (lane >= d) inc += o;
+        }
+        if (lane == 31) s_warp_terms[warp - 1] = inc;
+        if (my_quotes) atomicAdd(&s_quotes, my_quotes);
+        if (my_flags) atomicOr(&s_flags, my_flags);
+        ms_bar_workers(NW);
+        int before, total_terms;
+        {
+            const int mine_w = lane < WW ? s_warp_terms[lane] : 0;
+            int sc = mine_w;
+#pragma unroll
+            for (int d = 1; d < 16; d <<= 1) {
+                const int o = __shfl_up_sync(0xffffffffu, sc, d);
+                if (lane >= d) sc += o;
+            }
+            total_terms = __shfl_sync(0xffffffffu, sc, WW - 1);
+            before = __shfl_sync(0xffffffffu, sc - mine_w, warp - 1);
+        }
+        const int lt0 = before + inc - my_terms;  // terminators before my segments
+        if (lt_end_part >= 0) s_lt_end = lt0 + lt_end_part;
+        // local row L starts right after the L-th terminator of the region (L >= 1); row 0 starts at byte 0
+        {
+            int lt = lt0;
+            uint32_t hb = my_hits;
+            while (hb) {
+                const int k = __ffs(hb) - 1;
+                hb &= hb - 1u;
+                const int v = v0 + k;
+                uint32_t term = tmask[v];
+                while (term) {
+                    const int b2 = __ffs(term) - 1;
+                    term &= term - 1u;
+                    lt++;
+                    if (lt <= FUSED_ROWS_CAP + 1) row_start[lt] = (uint16_t)((v << 4) + b2 + 1);
+                }
+            }
+            if (wtid == 0) row_start[0] = 0;
+        }
+        ms_bar_workers(NW);
+
+        // ---- ownership: the rows that START in [t0, t0 + tile_len)
+        const bool starts_at_t0_w = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
+        lt_first = starts_at_t0_w ? 0 : 1;
+        lt_last = s_lt_end;  // inclusive; tile_len >= 1, so some worker set it
+        n_own = max(0, lt_last - lt_first + 1);
+        if (n_own > 0 && total_terms < lt_last + 1) fatal |= MS_LOAD_ROW_TOO_LONG;  // the last owned row does not end in the region
+        if (lt_last + 1 > FUSED_ROWS_CAP) fatal |= MS_LOAD_DENSE_ROWS;
+
+        // ---- P2. blank rows (section separators): every field empty after str.strip() (reader.py:886-901).  A
+        // data row starts with its frame number, so only rows that start with a comma or a blank are looked at in full.
+        if (!fatal) {
+            for (int L = lt_first + wtid; L <= lt_last; L += NW) {
+                const int p = row_start[L], e = row_start[L + 1];
+                const unsigned c = reg[p];
+                if (c == ',' || c <= 0x20u) {
+                    bool blank = true;
+                    for (int i = p; i < e; i++) {
+                        const unsigned b2 = reg[i];
+                        if (!(b2 == ',' || ms_is_strip_space(b2))) {
+                            blank = false;
+                            break;
+                        }
+                    }
+                    if (blank) {
+                        atomicAdd(&s_nblank, 1);
+                        atomicMin(&s_blank_lo, L);
+                        atomicMax(&s_blank_hi, L);
+                    }
+                }
+            }
+        }
+        ms_bar_workers(NW);
+        // ---- P3. tell the other tiles what this one holds
+        if (wtid == 0) {
+            const int nbw = s_nblank;
+            LbVal agg;
+            agg.nb = (uint32_t)min(nbw, 3);
+            agg.dist = (unsigned long long)(nbw ? lt_last - s_blank_hi : n_own);
+            if (tile > 0) st_relaxed_u64(&lb[tile], lb_pack(LB_AGGREGATE, agg));
+            s_agg_nb = agg.nb;
+            s_agg_dist = agg.dist;
+            s_fatal = fatal;
+            __threadfence_block();
+            *(volatile int*)&s_agg_ready = 1;
+            if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
+            const uint32_t f = s_flags | fatal | (nbw > 2 ? MS_LOAD_MANY_BLANKS : 0u);
+            if (f) atomicOr(&res->flags, f);
+        }
+        // delimiter mask of every segment = its commas (exact) + the line-end bytes P1b left
+        for (int v = wtid; v < nseg_; v += NW) {
             const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
             uint32_t cm = ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu), ms_eq_flags(x.z, 0x2c2c2c2cu),
                                     ms_eq_flags(x.w, 0x2c2c2c2cu));
@@ -565,13 +611,17 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             cmask[v] = (uint16_t)cm;
         }
     }
-    if (tid == 0) {
-        if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
-        const uint32_t f = s_flags | fatal | (nb > 2 ? MS_LOAD_MANY_BLANKS : 0u);
-        if (f) atomicOr(&res->flags, f);
-    }
     __syncthreads();
+    fatal = s_fatal;
     if (fatal) return;
+    {
+        const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
+        lt_first = starts_at_t0 ? 0 : 1;
+        lt_last = s_lt_end;
+        nb = s_nblank;
+        blank_lo = s_blank_lo;
+        blank_hi = s_blank_hi;
+    }
     const int pre_nb = (int)s_pre_nb;
     const long long pre_dist = (long long)s_pre_dist;
 
