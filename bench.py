@@ -1,27 +1,31 @@
 #!/usr/bin/env python
-"""Headline benchmark: Vicon CSV loader throughput (GB of CSV per second, output bit-exact)
-on synthetic 10-minute trials of the dynamic_trial.csv layout (BASELINE.json configs[1]).
+"""Headline benchmark: Vicon CSV loader throughput (GB of CSV per second, output bit-exact) on synthetic 10-minute
+trials of the dynamic_trial.csv layout (BASELINE.json configs[1]).
 
     python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
 
-One step = one pass of the hot path over one trial per GPU: ms_scan + header parse +
-ms_parse (all data rows -> channel-major float64 in HBM) + Segmenter (40 transitions) +
-gather of the 32 phase windows of the EMG device.  `value` times it with the CSV bytes already
-resident in HBM; `e2e` times the public batch call `ViconLoader.load_many` from pinned HOST
-bytes to HOST arrays (H2D of every CSV byte and D2H of every parsed double inside the timed
-region, overlapped across consecutive trials on three streams).
-Multi-GPU: one process per GPU, one distinct trial per rank per step, no collective on the
-data path (weak scaling); NCCL is used only for the barrier and the max-over-ranks time.
+One step = one pass of the hot path over one trial per GPU: the single-pass loader kernel (ms_load_fused: every data
+row of both sections -> channel-major float64 in HBM) + Segmenter (40 transitions) + gather of the 32 phase windows
+of the EMG device.  `value` times it with the CSV bytes already resident in HBM; `e2e` times the public batch call
+`ViconLoader.load_many` from pinned HOST bytes to HOST arrays (H2D of every CSV byte and D2H of every parsed double
+inside the timed region, overlapped across consecutive trials on three streams) and is set against what the box's
+PCIe links deliver with all ranks copying at once (`pcie`).  Multi-GPU: one process per GPU, trials sharded by file,
+no collective on the data path (weak scaling); NCCL carries only the barrier, the max-over-ranks time and the one
+host-side gather of result tables.  Besides the T10 step every rank also runs its shard of `configs[2]` (files in
+tmpfs -> host arrays) and `configs[4]` (files -> synergies).
 
-`--impl reference` times the reference's own CPU algorithm (oracle/vicon_oracle.py, the
-plain-Python port of load_vicon_file) on all host cores, on a bounded sample of the same
-layout.
+`--impl reference` times the UNMODIFIED reference (baseline/_ref, installed by oracle/install_ref.py):
+muscle_synergies.load_vicon_file + project/segment.py Segmenter + the 32 EMG phase windows per trial in a persistent
+multiprocessing.Pool over all host cores, on a bounded sample of the same layout; and scikit-learn's NMF(mu) over
+the same cores.
 """
 import argparse
 import json
 import os
+import shutil
 import subprocess
 import sys
+import tempfile
 import threading
 import time
 
@@ -31,50 +35,164 @@ sys.path.insert(0, ROOT)
 METRIC = "vicon_csv_loader_throughput"
 UNIT = "GB/s"
 WORKLOAD = "T10: synthetic 10-min Vicon trial, 2 force plates + 16 EMG @2 kHz, 40 markers @100 Hz, load + segment"
+SAMPLE_SECONDS = 6.0  # length of the trials of the CPU sample (T10 column layout, ~5 MB each)
 
 
-# ---- CPU baseline (the reference's algorithm, Python port, all cores) ------------------------------
-def _cpu_worker(args):
-    path, reps = args
+def shm_dir(need_bytes):
+    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > need_bytes else None
+    return base
+
+
+# ---- CPU arm: the reference itself ------------------------------------------------------------------------------
+def _ref_init():
+    global _REF
+    os.environ.setdefault("OMP_NUM_THREADS", "1")
+    os.environ.setdefault("OPENBLAS_NUM_THREADS", "1")
+    from oracle import refstub
+
+    _REF = refstub.import_reference()
+
+
+def _ref_trial(path):
+    """What one step does to one trial, by the reference: load_csv.py:96-135, project/segment.py:124-298,
+    user_data.py:727-731 (dev[slice] for the 32 phase windows of the EMG device)."""
+    ms_ref, seg_mod = _REF
+    data = ms_ref.load_vicon_file(path)
+    seg = seg_mod.Segmenter(data)
+    rows = 0
+    for trecho in seg_mod.Trecho:
+        for cycle in seg_mod.Cycle:
+            for phase in seg_mod.Phase:
+                rows += len(data.emg[seg.get_times_of(trecho, cycle, phase)])
+    return os.path.getsize(path), rows
+
+
+def _port_init():
+    pass
+
+
+def _port_trial(path):
     from oracle.vicon_oracle import load_vicon_file_oracle
 
-    n = 0
-    for _ in range(reps):
-        res = load_vicon_file_oracle(path)
-        n += res.num_frames
-    return n
+    res = load_vicon_file_oracle(path)
+    return os.path.getsize(path), res.num_frames
 
 
-def cpu_baseline(seconds_of_trial=6.0, target_wall=12.0, reps=None):
-    """Loads a `seconds_of_trial` T10-layout sample once per core per rep with the Python port of
-    the reference loader; returns (GB/s, cores, sample description, wall seconds)."""
-    import multiprocessing as mp
+def _nmf_task(args):
+    import warnings
 
-    from tools.synth_vicon import synth_vicon
+    from sklearn.decomposition import NMF
 
-    cores = os.cpu_count() or 1
-    blob = synth_vicon(seed=1234, seconds=seconds_of_trial, n_emg=16, n_markers=40)
-    base = "/dev/shm" if os.path.isdir("/dev/shm") else "/tmp"
-    path = os.path.join(base, f"ms_b200_cpu_sample_{os.getpid()}.csv")
-    blob.tofile(path)
-    try:
+    X, k, seed, iters = args
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        m = NMF(n_components=k, solver="mu", init="random", random_state=seed, max_iter=iters, tol=0.0)
+        m.fit_transform(X)
+    return int(m.n_iter_)
+
+
+class CpuArm:
+    """The reference's CPU implementation of the step over a persistent pool of all host cores."""
+
+    def __init__(self, cores=None):
+        import multiprocessing as mp
+
+        from oracle import refstub
+        from tools.synth_vicon import synth_vicon
+
+        self.cores = cores or len(os.sched_getaffinity(0))
+        self.kind = "reference" if refstub.reference_available() else "port"
+        n_files = max(16, self.cores)
+        self.tmp = tempfile.mkdtemp(prefix="ms_b200_cpu_", dir=shm_dir(n_files * (8 << 20)))
+        self.paths, self.bytes = [], 0
+        for i in range(n_files):
+            blob = synth_vicon(seed=5000 + i, seconds=SAMPLE_SECONDS, n_emg=16, n_markers=40)
+            path = os.path.join(self.tmp, f"sample{i}.csv")
+            blob.tofile(path)
+            self.paths.append(path)
+            self.bytes += int(blob.nbytes)
         ctx = mp.get_context("fork")
-        with ctx.Pool(cores) as pool:
-            pool.map(_cpu_worker, [(path, 1)] * cores)  # warm-up: imports, page cache
-            if reps is None:
-                t = time.perf_counter()
-                pool.map(_cpu_worker, [(path, 1)] * cores)
-                one = time.perf_counter() - t
-                reps = max(1, int(target_wall / max(one, 1e-3)))
-            t = time.perf_counter()
-            pool.map(_cpu_worker, [(path, reps)] * cores)
-            wall = time.perf_counter() - t
+        init, self.task = (_ref_init, _ref_trial) if self.kind == "reference" else (_port_init, _port_trial)
+        self.pool = ctx.Pool(self.cores, initializer=init)
+        what = ("unmodified reference: load_vicon_file + Segmenter + 32 EMG phase windows" if self.kind == "reference"
+                else "python port of load_vicon_file (load only; baseline/_ref is missing)")
+        self.sample = (f"{n_files} distinct {SAMPLE_SECONDS:g} s T10-layout trials ({self.bytes / n_files / 1e6:.1f} MB each) "
+                       f"per step over a persistent Pool({self.cores}); {what}")
+
+    def step(self):
+        t = time.perf_counter()
+        done = self.pool.map(self.task, self.paths, chunksize=1)
+        wall = time.perf_counter() - t
+        assert sum(b for b, _ in done) == self.bytes
+        return wall
+
+    def nmf(self, iters=200):
+        """sklearn NMF(mu) over the same pool: the (k, restart) grid of configs[3] on a 200 x 16 envelope matrix."""
+        X = nmf_envelopes()
+        grid = [(X, k, s, iters) for k in range(1, 9) for s in range(20)]
+        self.pool.map(_nmf_task, grid[: self.cores], chunksize=1)  # warm-up: imports
+        t = time.perf_counter()
+        n_iter = sum(self.pool.map(_nmf_task, grid, chunksize=1))
+        wall = time.perf_counter() - t
+        return {"iterations_per_s": n_iter / wall, "processes": self.cores, "problems": len(grid), "iterations_per_problem": iters,
+                "solver": "sklearn.decomposition.NMF(solver='mu', init='random', tol=0), float64"}
+
+    def close(self):
+        self.pool.close()
+        self.pool.join()
+        shutil.rmtree(self.tmp, ignore_errors=True)
+
+
+def cpu_baseline(target_wall=15.0):
+    """Bounded run of the CPU arm for the `cpu_baseline` object of our own line."""
+    arm = CpuArm()
+    try:
+        arm.step()  # warm-up: imports, page cache
+        walls = [arm.step()]
+        while sum(walls) < target_wall and len(walls) < 20:
+            walls.append(arm.step())
+        gbs = arm.bytes * len(walls) / sum(walls) / 1e9
+        return {"value": gbs, "unit": UNIT, "cores": arm.cores, "kind": arm.kind,
+                "sample": f"{len(walls)} steps of: {arm.sample}"}
     finally:
-        os.unlink(path)
-    total = blob.nbytes * reps * cores
-    sample = (f"{cores} processes x {reps} loads of a {seconds_of_trial:g} s T10-layout trial "
-              f"({blob.nbytes / 1e6:.1f} MB), python port of load_vicon_file")
-    return total / wall / 1e9, cores, sample, wall
+        arm.close()
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    arm = CpuArm()
+    try:
+        for _ in range(max(1, args.warmup)):
+            arm.step()
+        steps = max(1, args.steps)
+        walls = []
+        budget = time.perf_counter() + 240.0  # the whole run ends within a few minutes whatever --steps says
+        for _ in range(steps):
+            walls.append(arm.step())
+            if time.perf_counter() > budget:
+                break
+        t_total = sum(walls)
+        value = arm.bytes * len(walls) / t_total / 1e9
+        try:
+            nmf = arm.nmf()
+        except Exception as exc:  # noqa: BLE001
+            nmf = {"error": f"{type(exc).__name__}: {exc}"}
+        note = "" if len(walls) == steps else f"; stopped after {len(walls)} of {steps} steps (time budget)"
+        line = {
+            "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(walls), "warmup": max(1, args.warmup), "ms_per_step": 1e3 * t_total / len(walls),
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": WORKLOAD, "note": "the reference's own CPU implementation on a bounded sample per step" + note},
+            "cpu_baseline": {"value": value, "unit": UNIT, "cores": arm.cores, "kind": arm.kind, "sample": arm.sample},
+            "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+            "nmf": nmf,
+            "gpu_launches": 0,
+        }
+        print(json.dumps(line))
+    finally:
+        arm.close()
 
 
 # ---- clocks ---------------------------------------------------------------------------------------------
@@ -160,13 +278,13 @@ def nmf_envelopes(seed=1, n=200, m=16, k_true=4):
 
 
 def bench_nmf(dev, iters=2000):
-    """160 problems (k=1..8 x 20 restarts) x `iters` MU iterations in one launch; sklearn on one
-    core for a bounded subset beside it."""
-    import warnings
+    """160 problems (k=1..8 x 20 restarts) x `iters` MU iterations in one launch (configs[3]); and the long-signal
+    regime where X and W stream from HBM every iteration."""
+    import ctypes
 
-    import numpy as np
     import torch
 
+    from muscle_synergies_b200 import _native as nat
     from muscle_synergies_b200 import analysis
 
     X = nmf_envelopes()
@@ -174,8 +292,6 @@ def bench_nmf(dev, iters=2000):
     seeds = [r for _ in range(1, 9) for r in range(20)]
     analysis.nmf_mu_batched(X, ranks, seeds, max_iter=50, tol=0.0)  # warm-up
     torch.cuda.synchronize()
-    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    # time the launch itself: host init / upload excluded by timing a second, longer run around events
     t = time.perf_counter()
     res = analysis.nmf_mu_batched(X, ranks, seeds, max_iter=iters, tol=0.0)
     torch.cuda.synchronize()
@@ -189,15 +305,7 @@ def bench_nmf(dev, iters=2000):
     out = {"problems": len(ranks), "shape": [200, 16], "iterations_per_problem": iters,
            "iterations_per_s": total_iters / kernel_s, "kernel_s": kernel_s, "host_overhead_s": overhead,
            "regime": "shared-memory resident (no HBM traffic between iterations): bound by SM issue, not HBM"}
-    # long-signal variant: X and W stream from HBM every iteration (the 200 x 16 case never touches HBM).
-    # Timed with CUDA events around the C entry point on device-resident factors (the host-side upload of a
-    # 2 M-row initialisation would drown the kernels in a wall-clock measurement); two iteration counts, the
-    # difference is the cost of the extra iterations alone.
     try:
-        import ctypes
-
-        from muscle_synergies_b200 import _native as nat
-
         n_long, m, k, P = 2_000_000, 16, 8, 4
         lib = nat.lib()
         Xl = torch.rand((n_long, m), device=dev, dtype=torch.float32)
@@ -211,11 +319,11 @@ def bench_nmf(dev, iters=2000):
         stream = torch.cuda.current_stream(dev)
         sptr = ctypes.c_void_p(stream.cuda_stream)
 
-        def run(iters):
+        def run(n_it):
             W, H = W0.clone(), H0.clone()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record(stream)
-            nat.check(lib.ms_nmf_mu_stream(Xl.data_ptr(), n_long, m, ranks_c, None, P, W.data_ptr(), H.data_ptr(), iters,
+            nat.check(lib.ms_nmf_mu_stream(Xl.data_ptr(), n_long, m, ranks_c, None, P, W.data_ptr(), H.data_ptr(), n_it,
                                            ctypes.c_float(0.0), 10, work.data_ptr(), d_iter.data_ptr(), d_err.data_ptr(),
                                            d_vaf.data_ptr(), sptr), "ms_nmf_mu_stream")
             e1.record(stream)
@@ -227,128 +335,21 @@ def bench_nmf(dev, iters=2000):
         t_small = min(run(5) for _ in range(2))
         t_big = min(run(5 + its) for _ in range(2))
         per_iter = max(t_big - t_small, 1e-6) / its
-        bytes_iter = P * (4 * n_long * m + 8 * n_long * k)
+        shared_x = 4 * n_long * m + P * 8 * n_long * k  # X read once for all problems, W read + written per problem
         out["long_signal"] = {"shape": [n_long, m], "rank": k, "problems": P, "iterations_per_s": P / per_iter,
                               "ms_per_iteration_all_problems": per_iter * 1e3,
-                              "algorithmic_gbs": bytes_iter / per_iter / 1e9,
-                              "note": "4nm + 8nk bytes per iteration and problem; X re-read per problem; CUDA events"}
+                              "algorithmic_gbs": shared_x / per_iter / 1e9,
+                              "note": "algorithmic bytes per iteration = 4nm (X once for all problems of the launch) + P x 8nk; CUDA events"}
         del Xl, W0, H0
     except Exception as exc:  # noqa: BLE001
         out["long_signal"] = {"error": f"{type(exc).__name__}: {exc}"}
-    try:
-        from sklearn.decomposition import NMF
-
-        t = time.perf_counter()
-        done = 0
-        with warnings.catch_warnings():
-            warnings.simplefilter("ignore")
-            for k, s in list(zip(ranks, seeds))[::8]:
-                m = NMF(n_components=k, solver="mu", init="random", random_state=s, max_iter=200, tol=0.0)
-                m.fit_transform(X)
-                done += m.n_iter_
-        out["sklearn_iterations_per_s_1core"] = done / (time.perf_counter() - t)
-    except Exception as exc:  # noqa: BLE001
-        out["sklearn_iterations_per_s_1core"] = None
-        out["sklearn_error"] = str(exc)
     return out
-
-
-def bench_pipeline(loader, d_bytes, n, layout, trials=3):
-    """BASELINE configs[4] per trial: device-resident CSV -> load -> segment -> 8 gait cycles ->
-    envelopes -> NMF sweep k=1..8 x 20 restarts x 200 iterations (1280 problems, one launch);
-    wall clock, results (factors, errors, VAF of every restart) on the host."""
-    import torch
-
-    from muscle_synergies_b200.pipeline import trial_synergies
-
-    def one():
-        data = loader.load_device(d_bytes, n=n, name=layout)
-        return trial_synergies(data, 1, 8, n_restarts=20, random_state=0, max_iter=200, tol=0.0)
-
-    one()
-    torch.cuda.synchronize()
-    t = time.perf_counter()
-    for _ in range(trials):
-        res = one()
-    torch.cuda.synchronize()
-    per_trial = (time.perf_counter() - t) / trials
-    return {"workload": "per trial: load + segment + 8 cycles x (envelope, time-normalise 200) + NMF k=1..8 x 20 restarts x 200 it",
-            "cycles_per_s": len(res.cycles) / per_trial, "ms_per_trial": per_trial * 1e3,
-            "nmf_problems_per_trial": int(len(res.restarts)), "timing": "wall clock; factors, errors and VAF of every restart on the host (DataFrames are built on access)"}
-
-
-def bench_files(loader, blob, layout, copies=6):
-    """SURVEY.md section 8d, third number: files -> host arrays through `ViconLoader.load_files` (reader thread ->
-    pinned ring -> H2D / parse / D2H pipeline).  `copies` files of the trial in shared memory (or the temp
-    directory), page cache warm, wall clock."""
-    import shutil
-    import tempfile
-
-    import torch
-
-    base = "/dev/shm" if os.path.isdir("/dev/shm") and shutil.disk_usage("/dev/shm").free > (copies + 1) * blob.nbytes else None
-    tmp = tempfile.mkdtemp(prefix="ms_b200_bench_", dir=base)
-    try:
-        paths = []
-        for i in range(copies):
-            path = os.path.join(tmp, f"trial{i}.csv")
-            with open(path, "wb") as f:
-                f.write(memoryview(blob))
-            paths.append(path)
-
-        def run():
-            last = None
-            for _name, data in loader.load_files(paths, to_host=True):
-                if isinstance(data, Exception):
-                    raise data
-                last = data
-            for blk in last.blocks:
-                blk.host()
-            torch.cuda.synchronize()
-
-        run()
-        t = time.perf_counter()
-        run()
-        wall = time.perf_counter() - t
-        return {"value": copies * blob.nbytes / wall / 1e9, "unit": UNIT, "files": copies, "ms_per_file": wall / copies * 1e3,
-                "where": "tmpfs" if base else "temp directory", "api": "ViconLoader.load_files -> host arrays, wall clock"}
-    finally:
-        shutil.rmtree(tmp, ignore_errors=True)
-
-
-# ---- reference arm ----------------------------------------------------------------------------------------
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return
-    # each step: every core loads the sample once
-    vals = []
-    cores = os.cpu_count() or 1
-    for _ in range(args.warmup):
-        cpu_baseline(seconds_of_trial=3.0, reps=1)
-    t_total = 0.0
-    nbytes = 0.0
-    sample = ""
-    for _ in range(max(1, args.steps)):
-        gbs, cores, sample, wall = cpu_baseline(seconds_of_trial=3.0, reps=1)
-        vals.append(gbs)
-        t_total += wall
-        nbytes += gbs * wall
-    value = nbytes / t_total
-    line = {
-        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t_total / max(1, args.steps),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": WORKLOAD, "note": "reference CPU algorithm (python port) on a bounded sample per step"},
-        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
-    print(json.dumps(line))
 
 
 # ---- our arm ------------------------------------------------------------------------------------------------
 def run_ours(args):
+    import ctypes
+
     import numpy as np
     import torch
 
@@ -360,7 +361,7 @@ def run_ours(args):
     torch.cuda.set_device(local_rank)
     dev = torch.device(f"cuda:{local_rank}")
     # staging buffers and the threads that fill them next to the GPU (restored before the CPU baseline)
-    from muscle_synergies_b200.sharding import bind_to_gpu_numa
+    from muscle_synergies_b200.sharding import bind_to_gpu_numa, gather_results, shard
 
     all_cpus = os.sched_getaffinity(0)
     numa_cpus = bind_to_gpu_numa(local_rank)
@@ -379,44 +380,49 @@ def run_ours(args):
     import muscle_synergies_b200 as ms
     from muscle_synergies_b200 import _native
     from muscle_synergies_b200.segment import Segmenter
+    from muscle_synergies_b200.vicon_data import loader as loader_mod
     from tools.synth_vicon import synth_layout
 
     layout = args.layout
-    blob = synth_layout(layout, seed=1000 + rank)
+    blobs = [synth_layout(layout, seed=1000 + 2 * rank + i) for i in range(2)]  # two distinct trials per rank
+    blob = blobs[0]
     n = int(blob.nbytes)
     loader = ms.ViconLoader(dev)
-    pinned_in = torch.empty(loader.padded_size(n), dtype=torch.uint8, pin_memory=True)
-    pinned_in.numpy()[:n] = blob
+    pinned_in = []
+    for b in blobs:
+        p = torch.empty(loader.padded_size(int(b.nbytes)), dtype=torch.uint8, pin_memory=True)
+        p.numpy()[: b.nbytes] = b
+        pinned_in.append(p[: int(b.nbytes)])
     d_bytes = torch.empty(loader.padded_size(n), dtype=torch.uint8, device=dev)
-    d_bytes[:n].copy_(pinned_in[:n])
+    d_bytes[:n].copy_(pinned_in[0])
     torch.cuda.synchronize()
 
     def step_resident():
-        # one submission: parse, transition search and the gather of the 32 EMG phase windows are queued
-        # back to back; the parse status, the transitions and the window bounds come back in one wait
+        # one submission per stage: the single-pass loader kernel, then transition search + window plan + gather of
+        # the 32 EMG phase windows queued back to back
         data = loader.load_device(d_bytes, n=n, name=layout, defer_check=True)
         seg = Segmenter(data, cut_phases_of=(data.emg,))
         cuts = seg.phase_cuts(data.emg)
         return data, cuts
 
-    # shapes for the algorithmic byte count (SURVEY.md section 8d): B_alg = B_csv + 8 * N_kept
-    data, cuts = step_resident()
-    n_kept = sum(int(d.tensor.numel()) for d in list(data.forcepl) + [data.emg] + list(data.traj))
-    b_alg = n + 8 * n_kept
-
-    def run_e2e(steps):
-        """`steps` trials through the public pipelined API: pinned host CSV -> host arrays."""
-        last = None
-        for d in loader.load_many([pinned_in[:n]] * steps, names=[layout] * steps, to_host=True, host_slots=2):
-            last = d
-        for blk in last.blocks:
-            blk.host()
-        return last
-
     def barrier():
         if dist is not None:
             dist.barrier()
         torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def sum_over_ranks(x):
+        if dist is None:
+            return x
+        t = torch.tensor([x], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        return float(t.item())
 
     def timed(fn, steps):
         barrier()
@@ -426,41 +432,24 @@ def run_ours(args):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        ms_total = e0.elapsed_time(e1)
-        if dist is not None:
-            t = torch.tensor([ms_total], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms_total = float(t.item())
+        ms_total = max_over_ranks(e0.elapsed_time(e1))
         barrier()
         return ms_total
 
+    # shapes for the algorithmic byte count (SURVEY.md section 8d): B_alg = B_csv + 8 * N_kept
+    data, cuts = step_resident()
+    n_kept = sum(int(d.tensor.numel()) for d in list(data.forcepl) + [data.emg] + list(data.traj))
+    b_alg = n + 8 * n_kept
     for _ in range(max(3, args.warmup)):
         step_resident()
+    path_used = dict(loader.stats)
     launches0 = _native.launch_count()
     with ClockSampler(local_rank) as clocks:
         ms_total = timed(step_resident, args.steps)
     launches = _native.launch_count() - launches0
     value = world * n * args.steps / (ms_total * 1e-3) / 1e9
 
-    # ---- kernel-only timings on the launching stream (roofline of the dominant kernel)
-    import ctypes
-
-    from muscle_synergies_b200.vicon_data import loader as loader_mod
-
-    src = loader_mod._Source(d_bytes, n, None)
-    summary, ws = loader._scan(src)
-    plan = loader_mod._plan(src, summary, layout)
-    sections = (_native.Section * _native.MS_MAX_SECTIONS)()
-    blocks = []
-    k = 0
-    for lay, (r0, r1) in zip(plan.layouts, plan.data_rows):
-        blk = torch.empty((lay.n_keep, r1 - r0), dtype=torch.float64, device=dev)
-        blocks.append(blk)
-        s = sections[k]
-        s.row_begin, s.row_end, s.num_cols, s.n_keep, s.d_out, s.stride = r0, r1, lay.num_cols, lay.n_keep, blk.data_ptr(), r1 - r0
-        k += 1
-    d_status = torch.empty(1, dtype=torch.int64, device=dev)
-    d_summary = torch.empty(ctypes.sizeof(_native.ScanSummary), dtype=torch.uint8, device=dev)
+    # ---- kernel-only timings on the launching stream (roofline of the loader: ONE kernel reads the CSV and writes the arrays)
     stream = torch.cuda.current_stream()
     sptr = ctypes.c_void_p(stream.cuda_stream)
     lib = _native.lib()
@@ -477,57 +466,166 @@ def run_ours(args):
         torch.cuda.synchronize()
         return sum(a.elapsed_time(b) for a, b in evs) / reps
 
-    t_parse = time_kernel(lambda: lib.ms_parse(d_bytes.data_ptr(), n, ws.data_ptr(), sections, k, d_status.data_ptr(), sptr))
-    t_scan = time_kernel(lambda: lib.ms_scan(d_bytes.data_ptr(), n, ws.data_ptr(), ws.numel(), d_summary.data_ptr(), sptr))
-    assert int(d_status.item()) == -1, "parse reported an error on the benchmark input"
+    rows = [b.n_rows for b in data.blocks]
+    keep = [int(b.tensor.shape[0]) for b in data.blocks]
+    arena = torch.empty(keep[0] * (rows[0] + 64) + 2 + keep[1] * (rows[1] + 64), dtype=torch.float64, device=dev)
+    ws_bytes = int(lib.ms_load_workspace_bytes(n, 0))
+    ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
+    d_res = torch.empty(256 + 2 * _native.MS_LOAD_PEEK, dtype=torch.uint8, device=dev)
+    plan = _native.LoadPlan(arena.data_ptr(), arena.numel(), (ctypes.c_int64 * 2)(rows[0] + 64, rows[1] + 64), 0, 0)
+    t_fused = time_kernel(lambda: _native.check(lib.ms_load_fused(d_bytes.data_ptr(), n, ctypes.byref(plan), ws.data_ptr(), ws_bytes,
+                                                                   d_res.data_ptr(), d_res.data_ptr() + 256, sptr), "ms_load_fused"))
+    fres = _native.LoadResult.from_buffer_copy(d_res[: ctypes.sizeof(_native.LoadResult)].cpu().numpy().tobytes())
+    assert fres.flags == 0 and fres.status == _native.MS_ERR_NONE, "the single-pass kernel declined the benchmark input"
+    # the two-pass path (what answers for files the single-pass kernel declines), for comparison
+    src = loader_mod._Source(d_bytes, n, None)
+    summary, ws2 = loader._scan(src)
+    plan2 = loader_mod._plan(src, summary, layout)
+    sections = (_native.Section * _native.MS_MAX_SECTIONS)()
+    keepalive = []
+    k = 0
+    for lay, (r0, r1) in zip(plan2.layouts, plan2.data_rows):
+        blk = torch.empty((lay.n_keep, r1 - r0), dtype=torch.float64, device=dev)
+        keepalive.append(blk)
+        s = sections[k]
+        s.row_begin, s.row_end, s.num_cols, s.n_keep, s.d_out, s.stride = r0, r1, lay.num_cols, lay.n_keep, blk.data_ptr(), r1 - r0
+        k += 1
+    d_status = torch.empty(1, dtype=torch.int64, device=dev)
+    d_summary = torch.empty(ctypes.sizeof(_native.ScanSummary), dtype=torch.uint8, device=dev)
+    t_parse = time_kernel(lambda: lib.ms_parse(d_bytes.data_ptr(), n, ws2.data_ptr(), sections, k, d_status.data_ptr(), sptr))
+    t_scan = time_kernel(lambda: lib.ms_scan(d_bytes.data_ptr(), n, ws2.data_ptr(), ws2.numel(), d_summary.data_ptr(), sptr))
+    del keepalive, ws2, arena
 
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     if os.path.exists(peaks_path):
         peak, peak_src = float(json.load(open(peaks_path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
     else:
         peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
-    achieved = b_alg / (t_parse * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "parse_traffic.json")
+    achieved = b_alg / (t_fused * 1e-3) / 1e9
+    traffic, traffic_src = None, None
+    tpath = os.path.join(ROOT, "profiles", "r02_load_traffic.json")
     if os.path.exists(tpath):
-        traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
+        tj = json.load(open(tpath))
+        traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+
+    # ---- what the PCIe links deliver with every rank copying both ways at once (the ceiling of `e2e`)
+    def pcie_probe(mb=256, reps=8):
+        h_in = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True)
+        h_out = torch.empty(mb << 20, dtype=torch.uint8, pin_memory=True)
+        d_in = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+        d_out = torch.empty(mb << 20, dtype=torch.uint8, device=dev)
+        s1, s2 = torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+        out = {}
+        for name, up, down in (("h2d_alone", True, False), ("d2h_alone", False, True), ("both", True, True)):
+            barrier()
+            t = time.perf_counter()
+            for _ in range(reps):
+                if up:
+                    with torch.cuda.stream(s1):
+                        d_in.copy_(h_in, non_blocking=True)
+                if down:
+                    with torch.cuda.stream(s2):
+                        h_out.copy_(d_out, non_blocking=True)
+            torch.cuda.synchronize()
+            wall = max_over_ranks(time.perf_counter() - t)
+            out[name] = world * reps * (mb << 20) / wall / 1e9  # aggregate GB/s per direction
+        return out
+
+    pcie = pcie_probe()
 
     # ---- end to end from host memory: the public batch API, H2D / compute / D2H overlapped
+    def run_e2e(steps):
+        """`steps` trials through the public pipelined API: pinned host CSV -> host arrays."""
+        last = None
+        srcs = [pinned_in[i % 2] for i in range(steps)]
+        for d in loader.load_many(srcs, names=[layout] * steps, to_host=True):
+            last = d
+        for blk in last.blocks:
+            blk.host()
+        return last
+
     run_e2e(3)
     e2e_steps = max(4, min(args.steps, 8))
     barrier()
     t_e2e = time.perf_counter()
     run_e2e(e2e_steps)
     torch.cuda.synchronize()
-    ms_e2e = (time.perf_counter() - t_e2e) * 1e3
-    if dist is not None:
-        t = torch.tensor([ms_e2e], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_e2e = float(t.item())
+    ms_e2e = max_over_ranks((time.perf_counter() - t_e2e) * 1e3)
     e2e_value = world * n * e2e_steps / (ms_e2e * 1e-3) / 1e9
     d2h = int(8 * n_kept)
+    # per trial the links carry n bytes up and d2h bytes down at the same time
+    ceiling = n / max(n / (pcie["both"] / world * 1e9), d2h / (pcie["both"] / world * 1e9)) * world / 1e9
+
+    # ---- configs[2] and configs[4]: distinct trial files in tmpfs, sharded by file over the ranks
+    files_leg, pipeline_leg = None, None
+    try:
+        per_rank = 8
+        n_files = per_rank * world
+        base = shm_dir((n_files + 2) * (110 << 20))
+        tmp_root = os.path.join(base or tempfile.gettempdir(), f"ms_b200_bench_{os.environ.get('MASTER_PORT', 'single')}")
+        os.makedirs(tmp_root, exist_ok=True)
+        paths = [os.path.join(tmp_root, f"trial{i:03d}.csv") for i in range(n_files)]
+        sizes = []
+        for i in range(rank, n_files, world):  # every rank writes its share of the files; all ranks see the directory
+            synth_layout("T127", seed=2000 + i).tofile(paths[i])
+        barrier()
+        sizes = [os.path.getsize(p) for p in paths]
+        mine = shard(paths, rank, world, sizes)
+        my_bytes = sum(os.path.getsize(p) for p in mine)
+
+        def run_files():
+            last = None
+            for _name, d in loader.load_files(mine, to_host=True):
+                if isinstance(d, Exception):
+                    raise d
+                last = d
+            for blk in last.blocks:
+                blk.host()
+            torch.cuda.synchronize()
+
+        run_files()
+        barrier()
+        t = time.perf_counter()
+        run_files()
+        wall = max_over_ranks(time.perf_counter() - t)
+        files_leg = {"value": sum(sizes) / wall / 1e9, "unit": UNIT, "files": n_files, "files_per_rank": len(mine),
+                     "mb_per_file": sizes[0] / 1e6, "ms_per_file_per_rank": wall / max(1, len(mine)) * 1e3,
+                     "where": "tmpfs" if base else "temp directory", "bytes_this_rank": my_bytes,
+                     "api": "ViconLoader.load_files (reader thread -> pinned ring -> H2D / parse / D2H) -> host arrays; "
+                            "distinct T127 trials sharded by size over the ranks; wall clock, max over ranks"}
+
+        from muscle_synergies_b200.pipeline import synergies_for_files_sharded
+
+        kw = dict(min_components=1, max_components=8, n_restarts=20, random_state=0, max_iter=200, tol=0.0)
+        synergies_for_files_sharded(paths[: world], loader=loader, **kw)  # warm-up: one file per rank
+        barrier()
+        t = time.perf_counter()
+        table = synergies_for_files_sharded(paths, loader=loader, **kw)  # includes the host-side gather of the tables
+        wall = max_over_ranks(time.perf_counter() - t)
+        ok_rows = [r for r in table if "error" not in r]
+        n_cycles = len({(r["file"], r["trecho"], r["cycle"]) for r in ok_rows})
+        pipeline_leg = {"workload": "configs[4]: per trial load + segment + 8 gait cycles x (RMS envelope, time-normalise 200) + NMF "
+                                    "k=1..8 x 20 restarts x 200 it; best-of-restarts VAF tables gathered on the host",
+                        "trials": n_files, "cycles": n_cycles, "cycles_per_s": n_cycles / wall, "ms_per_trial_per_rank": wall / per_rank * 1e3,
+                        "table_rows": len(table), "failed_files": len(table) - len(ok_rows),
+                        "timing": "wall clock, max over ranks, files in tmpfs"}
+        barrier()
+        if rank == 0:
+            shutil.rmtree(tmp_root, ignore_errors=True)
+    except Exception as exc:  # noqa: BLE001
+        files_leg = files_leg or {"error": f"{type(exc).__name__}: {exc}"}
+        pipeline_leg = pipeline_leg or {"error": f"{type(exc).__name__}: {exc}"}
 
     # ---- NMF-MU extension: rank sweep k=1..8 x 20 restarts on 200 x 16 envelopes (configs[3])
     nmf = bench_nmf(dev) if rank == 0 else None
-    pipeline = None
-    if rank == 0:
-        try:
-            pipeline = bench_pipeline(loader, d_bytes, n, layout)
-        except Exception as exc:  # noqa: BLE001
-            pipeline = {"error": f"{type(exc).__name__}: {exc}"}
-
-    from_files = None
-    if rank == 0 and world == 1:
-        try:
-            from_files = bench_files(loader, blob, layout)
-        except Exception as exc:  # noqa: BLE001
-            from_files = {"error": f"{type(exc).__name__}: {exc}"}
 
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu:
         os.sched_setaffinity(0, all_cpus)
-        gbs, cores, sample, _wall = cpu_baseline()
-        cpu = {"value": gbs, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample}
+        try:
+            cpu = cpu_baseline()
+        except Exception as exc:  # noqa: BLE001
+            cpu = {"error": f"{type(exc).__name__}: {exc}"}
 
     if rank == 0:
         line = {
@@ -537,20 +635,23 @@ def run_ours(args):
             "config": {
                 "workload": WORKLOAD if layout == "T10" else layout, "csv_bytes_per_gpu": n, "kept_doubles_per_gpu": n_kept,
                 "l2": "input (CSV) and output are each larger than the 126 MB L2; no explicit flush",
-                "parallelism": f"{world} ranks, one trial per rank per step, no data-path collective",
+                "parallelism": f"{world} ranks, trials sharded by file, no data-path collective",
                 "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
+                "loader_path": path_used,
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
-                    "api": "ViconLoader.load_many(pinned host CSV) -> host arrays, 3-stream pipeline, wall clock"},
+                    "pcie_ceiling": ceiling, "frac_of_pcie_ceiling": e2e_value / ceiling,
+                    "api": "ViconLoader.load_many(pinned host CSV) -> host arrays, 3-stream pipeline, wall clock, two distinct trials alternating"},
+            "pcie": dict(pcie, unit="GB/s aggregate per direction, all ranks copying at once (256 MB pinned buffers)"),
             "gpu_launches": int(launches),
-            "roofline": {"bound": "hbm", "kernel": "ms_parse_kernel", "achieved": achieved, "peak": peak, "unit": "GB/s",
-                         "frac": achieved / peak, "traffic": traffic, "peak_source": peak_src,
-                         "algorithmic_bytes_per_launch": b_alg, "kernel_ms": t_parse},
-            "kernels_ms": {"ms_parse": t_parse, "ms_scan+resolve": t_scan},
+            "roofline": {"bound": "hbm", "kernel": "ms_load_kernel (the whole loader: CSV bytes -> float64 blocks)", "achieved": achieved,
+                         "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic, "traffic_source": traffic_src,
+                         "peak_source": peak_src, "algorithmic_bytes_per_launch": b_alg, "kernel_ms": t_fused},
+            "kernels_ms": {"ms_load_fused": t_fused, "two_pass": {"ms_parse": t_parse, "ms_scan+resolve": t_scan}},
             "nmf": nmf,
-            "pipeline": pipeline,
-            "from_files": from_files,
+            "files": files_leg,
+            "pipeline": pipeline_leg,
             "cpu_baseline": cpu,
             "clocks": clocks.summary(),
         }

@@ -22,7 +22,7 @@ from .emg import (  # noqa: F401
     time_normalize,
     zero_center,
 )
-from .pipeline import synergies_for_files, trial_synergies  # noqa: F401
+from .pipeline import synergies_for_files, synergies_for_files_sharded, trial_synergies  # noqa: F401
 from .vicon_data import (  # noqa: F401
     DeviceData,
     DeviceType,
@@ -56,4 +56,5 @@ __all__ = (
     "load_vicon_file_cached",
     "trial_synergies",
     "synergies_for_files",
+    "synergies_for_files_sharded",
 )

@@ -300,6 +300,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     }
     __syncthreads();
     const long long tile = (long long)s_tile;
+#if defined(FUSED_ABLATE) && FUSED_ABLATE == 1
+    return;  // launch + ticket only
+#endif
     const int tile_bytes = args.tile_bytes, region = args.region_bytes;
     const long long t0 = tile * (long long)tile_bytes;
     const int tile_len = (int)min((long long)tile_bytes, n - t0);
@@ -362,6 +365,22 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     // staging and P1/P2 of the other warps instead of after them (measured: a third of a block's lifetime went by
     // with all sixteen warps parked behind the look-back).  Warps 1.. (the "workers", synchronised among themselves
     // on named barrier 1) find this tile's rows and publish its aggregate as soon as it is known.
+#if defined(FUSED_ABLATE) && FUSED_ABLATE == 2
+    {  // + staging: wait for the bulk copy, nothing else
+        const uint32_t bar = (uint32_t)__cvta_generic_to_shared(&s_stage_bar);
+        uint32_t done = 0;
+        while (!done) {
+            asm volatile(
+                "{\n.reg .pred p;\n"
+                "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], 0;\n"
+                "selp.u32 %0, 1, 0, p;\n}\n"
+                : "=r"(done)
+                : "r"(bar)
+                : "memory");
+        }
+        return;
+    }
+#endif
     constexpr int NW = FUSED_THREADS - 32, WW = FUSED_WARPS - 1;
     const int wtid = tid - 32;
     const int nseg_ = nseg;
@@ -614,6 +633,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     __syncthreads();
     fatal = s_fatal;
     if (fatal) return;
+#if defined(FUSED_ABLATE) && FUSED_ABLATE == 3
+    return;  // + rows, look-back, delimiter masks; no parsing
+#endif
     {
         const bool starts_at_t0 = (t0 == 0) || reg[-1] == '\n' || (reg[-1] == '\r' && reg[0] != '\n');
         lt_first = starts_at_t0 ? 0 : 1;

@@ -101,13 +101,17 @@ def cycle_windows(segmenter: Segmenter) -> List[Tuple[Trecho, Cycle, slice]]:
 
 def trial_synergies(data: ViconNexusData, min_components: int = 1, max_components: int = 8, n_restarts: int = 20,
                     random_state: int = 0, max_iter: int = 200, tol: float = 1e-4, window_size: float = 0.5,
-                    reduce_to: int = 200, segmenter: Optional[Segmenter] = None, keep_batch: bool = False) -> TrialSynergies:
+                    reduce_to: int = 200, segmenter: Optional[Segmenter] = None, keep_batch: bool = False,
+                    seeds: Optional[Sequence[int]] = None) -> TrialSynergies:
     """Segments a loaded trial and factorises the EMG envelope of each of its 8 gait cycles for
     every rank in [min_components, max_components] from `n_restarts` random initialisations
-    (seeds random_state .. random_state + n_restarts - 1, sklearn `init="random"` draws)."""
+    (seeds random_state .. random_state + n_restarts - 1, sklearn `init="random"` draws; `seeds` names
+    them explicitly instead - the share of one GPU when the restarts of a trial are split over several)."""
     muscles = data.emg.columns
     if not 1 <= min_components <= max_components <= len(muscles):
         raise ValueError("invalid number of components")
+    seed_list = np.arange(random_state, random_state + n_restarts, dtype=np.int64) if seeds is None else np.asarray(list(seeds), dtype=np.int64)
+    n_restarts = int(seed_list.shape[0])
     if n_restarts < 1:
         raise ValueError("n_restarts must be positive")
     seg = segmenter if segmenter is not None else Segmenter(data)
@@ -117,7 +121,7 @@ def trial_synergies(data: ViconNexusData, min_components: int = 1, max_component
     n_cyc, n_k = len(wins), len(sweep)
     # problem order: cycle-major, then rank, then restart
     ranks = np.tile(np.repeat(np.array(sweep, dtype=np.int32), n_restarts), n_cyc)
-    seeds = np.tile(np.arange(random_state, random_state + n_restarts, dtype=np.int64), n_cyc * n_k)
+    seeds = np.tile(seed_list, n_cyc * n_k)
     x_index = np.repeat(np.arange(n_cyc, dtype=np.int32), n_k * n_restarts)
     res = nmf_mu_batched(env, ranks, seeds, max_iter=max_iter, tol=tol, x_index=x_index)
 
@@ -160,3 +164,82 @@ def synergies_for_files(paths: Sequence[str], loader: Optional[ViconLoader] = No
             yield path, trial_synergies(data, **kwargs)
         except (ValueError, IndexError, KeyError) as exc:  # e.g. fewer than 40 transitions in the trial
             yield path, exc
+
+
+# ---- several GPUs: one process per GPU, no collective on the data path ---------------------
+def best_restart_table(path: str, trial: TrialSynergies) -> List[dict]:
+    """The small per-trial result that travels between ranks: for every (cycle, rank) the best restart's seed,
+    iteration count, reconstruction error and VAF row ("All signals" + muscles; analysis.py:642-667)."""
+    rows = []
+    for c in trial.cycles:
+        for i, k in enumerate(c.components):
+            rows.append({"file": path, "trecho": c.trecho.value, "cycle": c.cycle.value, "n_components": int(k),
+                         "random_state": c.random_state[k], "n_iter": c.n_iter[k],
+                         "reconstruction_err": c.reconstruction_err[k], "vaf": np.asarray(c._vaf[i], dtype=np.float64)})
+    return rows
+
+
+def merge_tables(tables: Iterable[List[dict]]) -> List[dict]:
+    """Union of the ranks' tables; where several ranks hold the same (file, cycle, rank) - a trial whose restarts
+    were split over the GPUs - the restart with the smallest reconstruction error wins (ties: smallest seed)."""
+    best = {}
+    for table in tables:
+        for row in table:
+            if "error" in row:
+                best.setdefault((row["file"], "error"), row)
+                continue
+            key = (row["file"], row["trecho"], row["cycle"], row["n_components"])
+            cur = best.get(key)
+            if cur is None or (row["reconstruction_err"], row["random_state"]) < (cur["reconstruction_err"], cur["random_state"]):
+                best[key] = row
+    return [best[k] for k in sorted(best, key=lambda k: tuple(str(x) for x in k))]
+
+
+def synergies_for_files_sharded(paths: Sequence[str], rank: Optional[int] = None, world: Optional[int] = None,
+                                loader: Optional[ViconLoader] = None, gather: bool = True, analyse=None,
+                                n_restarts: int = 20, random_state: int = 0, **kwargs) -> List[dict]:
+    """`synergies_for_files` over the GPUs of one box.  Work is split with no exchange on the data path:
+
+      * at least as many files as GPUs: by file, balanced by size (`sharding.shard`); every rank loads, segments
+        and factorises its own trials;
+      * fewer files than GPUs: by (rank, restart) - every rank loads every file and runs the restarts
+        r with r % world == rank (the envelopes are recomputed rather than moved: a trial loads in
+        milliseconds, and nothing crosses NVLink).
+
+    Then ONE host-side gather of the small result tables (`sharding.gather_results`, torch.distributed object
+    gather) and the best-of-restarts merge.  Returns, on every rank, the merged table: one dict per (file, trecho,
+    cycle, n_components), or {"file", "error"} for a file that failed.  rank / world default to the process group's;
+    `analyse(paths, **kw)` is the per-file generator (default `synergies_for_files`; tests inject a CPU stand-in)."""
+    import os
+
+    from .sharding import gather_results, shard
+
+    if rank is None or world is None:
+        import torch.distributed as dist
+
+        if dist.is_available() and dist.is_initialized():
+            rank, world = dist.get_rank(), dist.get_world_size()
+        else:
+            rank, world = 0, 1
+    paths = [str(p) for p in paths]
+    analyse = analyse if analyse is not None else synergies_for_files
+    if len(paths) >= world:
+        sizes = [os.path.getsize(p) if os.path.exists(p) else 0 for p in paths]
+        mine = shard(paths, rank, world, sizes)
+        seeds = list(range(random_state, random_state + n_restarts))
+    else:
+        mine = paths
+        seeds = [random_state + r for r in range(n_restarts) if r % world == rank]
+    table: List[dict] = []
+    if mine and seeds:
+        kw = dict(kwargs)
+        if loader is not None:
+            kw["loader"] = loader
+        for path, result in analyse(mine, seeds=seeds, **kw):
+            if isinstance(result, Exception):
+                table.append({"file": path, "error": f"{type(result).__name__}: {result}"})
+            else:
+                table += best_restart_table(path, result)
+    if not gather:
+        return table
+    return merge_tables(gather_results(table))

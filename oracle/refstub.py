@@ -6,18 +6,29 @@ src/muscle_synergies/vicon_data/user_data.py:31, project/segment.py:8-9); neithe
 installed here, so four empty stand-in modules are registered before the import.
 Nothing in the loader / segmenter / NMF-wrapper code paths touches them.
 
-/root/reference does not exist on the GPU box: only `oracle/make_golden.py` and the
-`reference`-marked CPU tests use this module, and they skip when it is absent.
+/root/reference does not exist on the GPU box: `oracle/make_golden.py` and the `reference`-marked CPU
+tests use this module here and skip when it is absent; `bench.py --impl reference` (and the cpu_baseline
+leg) use the pip-installed copy under baseline/_ref/ (oracle/install_ref.py), which travels.
 """
 import os
 import sys
 import types
 
 REFERENCE_ROOT = os.environ.get("MS_REFERENCE_ROOT", "/root/reference")
+# the pip-installed copy that travels to the GPU box (oracle/install_ref.py): package and segment.py side by side
+INSTALLED_ROOT = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "baseline", "_ref")
+
+
+def _paths():
+    if os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "muscle_synergies")):
+        return [os.path.join(REFERENCE_ROOT, "src"), os.path.join(REFERENCE_ROOT, "project")]
+    if os.path.isfile(os.path.join(INSTALLED_ROOT, "muscle_synergies", "__init__.py")):
+        return [INSTALLED_ROOT]
+    return []
 
 
 def reference_available() -> bool:
-    return os.path.isdir(os.path.join(REFERENCE_ROOT, "src", "muscle_synergies"))
+    return bool(_paths())
 
 
 def _install_stubs():
@@ -55,9 +66,9 @@ def _install_stubs():
 def import_reference():
     """Returns (muscle_synergies, segment) modules of the reference, unmodified."""
     if not reference_available():
-        raise RuntimeError(f"reference not found under {REFERENCE_ROOT}")
+        raise RuntimeError(f"reference not found under {REFERENCE_ROOT} or {INSTALLED_ROOT}")
     _install_stubs()
-    for p in (os.path.join(REFERENCE_ROOT, "src"), os.path.join(REFERENCE_ROOT, "project")):
+    for p in _paths():
         if p not in sys.path:
             sys.path.insert(0, p)
     import muscle_synergies  # type: ignore

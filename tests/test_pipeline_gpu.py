@@ -114,3 +114,32 @@ def test_synergies_for_files(ms, tmp_path):
         assert len(res.cycles) == 8
         v = res.cycles[0].vaf_values["All signals"]
         assert 0.0 < v.loc[2] <= v.loc[3] + 1e-4 <= 1.0 + 1e-4
+
+
+def test_sharded_pipeline_matches_single_process(tmp_path):
+    """synergies_for_files_sharded with the ranks played one after the other in this process: by file (3 files over
+    2 ranks) and by (rank, restart) (1 file over 2 ranks).  The merged table equals the single-process one."""
+    import numpy as np
+
+    from muscle_synergies_b200.pipeline import merge_tables, synergies_for_files_sharded
+    from tools.synth_vicon import synth_vicon
+
+    paths = []
+    for i in range(3):
+        path = str(tmp_path / f"trial{i}.csv")
+        synth_vicon(seed=300 + i, seconds=8.0 + i, n_emg=16, n_markers=4).tofile(path)
+        paths.append(path)
+    kw = dict(min_components=2, max_components=3, n_restarts=4, random_state=5, max_iter=60, tol=0.0)
+    for subset in (paths, paths[:1]):
+        single = synergies_for_files_sharded(subset, rank=0, world=1, gather=False, **kw)
+        parts = [synergies_for_files_sharded(subset, rank=r, world=2, gather=False, **kw) for r in range(2)]
+        if len(subset) >= 2:
+            assert not ({row["file"] for row in parts[0]} & {row["file"] for row in parts[1]})  # a file has one owner
+        else:
+            assert parts[0] and parts[1]  # both ranks worked on the one file (different restarts)
+        merged = merge_tables(parts)
+        assert len(merged) == len(single) == len(subset) * 8 * 2
+        for a, b in zip(merged, single):
+            assert (a["file"], a["trecho"], a["cycle"], a["n_components"]) == (b["file"], b["trecho"], b["cycle"], b["n_components"])
+            assert a["random_state"] == b["random_state"] and a["n_iter"] == b["n_iter"]
+            assert np.array_equal(a["vaf"], b["vaf"]) and a["reconstruction_err"] == b["reconstruction_err"]
