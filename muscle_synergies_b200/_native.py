@@ -156,5 +156,29 @@ def check(code: int, what: str):
         raise NativeError(f"{what} failed: {names.get(code, code)} {detail}".strip())
 
 
+def on_tensor_device(fn):
+    """Runs `fn` with the CUDA device of its first tensor argument (or of the `.tensor` of a DeviceData) current.
+    The C entry points launch on the runtime's current device: a tensor on cuda:1 handed to them while cuda:0 is
+    current would fail (invalid resource handle) or touch the wrong device's memory."""
+    import functools
+
+    @functools.wraps(fn)
+    def wrapper(*args, **kwargs):
+        import torch
+
+        dev = None
+        for a in list(args) + list(kwargs.values()):
+            t = a if isinstance(a, torch.Tensor) else getattr(a, "__dict__", {}).get("_block") and a.tensor
+            if isinstance(t, torch.Tensor) and t.is_cuda:
+                dev = t.device
+                break
+        if dev is None:
+            return fn(*args, **kwargs)
+        with torch.cuda.device(dev):
+            return fn(*args, **kwargs)
+
+    return wrapper
+
+
 def launch_count() -> int:
     return int(lib().ms_launch_count())

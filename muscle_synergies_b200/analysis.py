@@ -210,6 +210,26 @@ class SynergyRunResult:
     transformed: Union[np.ndarray, Mapping[int, np.ndarray], None] = field(default=None, repr=False)
 
 
+def _find_synergies_sklearn(processed_emg_df, n_components, max_components, **sklearn_kwargs) -> "SynergyRunResult":
+    """find_synergies as the reference runs it (analysis.py:848-914): one sklearn.decomposition.NMF per rank."""
+    from sklearn.decomposition import NMF
+
+    def single(k):
+        model = NMF(n_components=k, **sklearn_kwargs)
+        transformed = model.fit_transform(processed_emg_df)
+        values = vaf(processed_emg_df, components=model.components_, transformed_signal=transformed)
+        comps = pandas.DataFrame(model.components_, columns=processed_emg_df.columns)
+        return SynergyRunResult(values, comps, model, transformed)
+
+    if max_components is None:
+        return single(n_components)
+    runs = OrderedDict((k, single(k)) for k in range(n_components, max_components + 1))
+    vaf_values = pandas.concat([r.vaf_values for r in runs.values()])
+    vaf_values.set_index(np.array(tuple(runs.keys())), inplace=True)
+    return SynergyRunResult(vaf_values, {k: r.components for k, r in runs.items()}, {k: r.model for k, r in runs.items()},
+                            {k: r.transformed for k, r in runs.items()})
+
+
 def find_synergies(
     processed_emg_df: pandas.DataFrame,
     n_components: int,
@@ -222,9 +242,10 @@ def find_synergies(
 ) -> SynergyRunResult:
     """Find muscle synergies with NMF (analysis.py:713-914) - all ranks and restarts in one launch.
 
-    Accepted scikit-learn keywords: solver="mu", init="random", beta_loss="frobenius" (or 2),
-    random_state=int.  `n_restarts` (extension) runs seeds random_state .. random_state+R-1 per
-    rank and keeps, per rank, the restart with the smallest reconstruction error."""
+    solver="mu", init="random", beta_loss="frobenius" (or 2), random_state=int run on the GPU, all ranks and
+    restarts in one launch; `n_restarts` (extension) runs seeds random_state .. random_state+R-1 per rank and keeps,
+    per rank, the restart with the smallest reconstruction error.  Any other scikit-learn configuration (the
+    default solver="cd", nndsvd inits, regularisation ...) is forwarded to scikit-learn as the reference does."""
     if processed_emg_df.empty:
         raise ValueError("empty EMG DataFrame")
     num_features = len(processed_emg_df.columns)
@@ -237,13 +258,15 @@ def find_synergies(
     init = kw.pop("init", None)
     beta_loss = kw.pop("beta_loss", "frobenius")
     seed = kw.pop("random_state", None)
-    if solver != "mu" or init != "random" or beta_loss not in ("frobenius", 2, 2.0):
-        raise NotImplementedError(
-            'the CUDA stage implements NMF(solver="mu", init="random", beta_loss="frobenius") only; '
-            "pass those keywords (the reference forwards them to scikit-learn)"
-        )
-    if kw:
-        raise NotImplementedError(f"unsupported NMF keywords: {sorted(kw)}")
+    if solver != "mu" or init != "random" or beta_loss not in ("frobenius", 2, 2.0) or kw:
+        # Everything the batched kernels do not implement is what the reference itself does with it: the keywords go
+        # to scikit-learn unchanged (analysis.py:848-864) - solver="cd" with an nndsvd* init is the tutorial's own call
+        # (docs/source/tutorials/Finding muscle synergies.ipynb, cell 26).  This is the reference's code path, not a
+        # fallback of the accelerated one: solver="mu", init="random" never comes here.
+        if n_restarts != 1:
+            raise ValueError("n_restarts is an extension of the batched mu solver; scikit-learn runs one initialisation")
+        return _find_synergies_sklearn(processed_emg_df, n_components, max_components, max_iter=max_iter, tol=tol,
+                                       **sklearn_kwargs)
     if seed is None:
         seed = int(np.random.randint(0, 2**31 - 1))
     ranks_sweep = [n_components] if max_components is None else list(range(n_components, max_components + 1))

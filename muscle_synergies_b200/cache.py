@@ -189,12 +189,18 @@ def cache_path_for(csv_filename, cache_dir=None) -> str:
     csv_filename = os.fspath(csv_filename)
     if cache_dir is None:
         return csv_filename + ".msb200"
-    return os.path.join(os.fspath(cache_dir), os.path.basename(csv_filename) + ".msb200")
+    # same-named trials of different directories must not share a cache file: the absolute path is part of the name
+    import hashlib
+
+    tag = hashlib.sha1(os.path.abspath(csv_filename).encode()).hexdigest()[:12]
+    return os.path.join(os.fspath(cache_dir), f"{os.path.basename(csv_filename)}.{tag}.msb200")
 
 
-def load_vicon_file_cached(csv_filename, cache_dir=None, loader=None, verify: bool = False) -> ViconNexusData:
-    """`load_vicon_file` with a binary cache beside the CSV (or in `cache_dir`): the cache is used when
-    it records the CSV's current size and mtime, otherwise the CSV is parsed and the cache rewritten."""
+def load_vicon_file_cached(csv_filename, cache_dir=None, loader=None, verify: bool = True) -> ViconNexusData:
+    """`load_vicon_file` with a binary cache beside the CSV (or in `cache_dir`): the cache is used when it
+    records this CSV's absolute path, current size and mtime, otherwise the CSV is parsed and the cache rewritten.
+    `verify` checks the CRC32 of every block read from the cache (a damaged cache is rebuilt from the CSV).  A
+    cache that cannot be written (read-only directory) is not an error: the parsed data is returned all the same."""
     from .vicon_data.loader import _default_loader
 
     st = os.stat(csv_filename)
@@ -203,10 +209,14 @@ def load_vicon_file_cached(csv_filename, cache_dir=None, loader=None, verify: bo
     if os.path.exists(cpath):
         try:
             src = read_trial_header(cpath).get("source") or {}
-            if src.get("size") == stamp["size"] and src.get("mtime_ns") == stamp["mtime_ns"]:
+            if (src.get("path") == stamp["path"] and src.get("size") == stamp["size"]
+                    and src.get("mtime_ns") == stamp["mtime_ns"]):
                 return load_trial(cpath, device=loader.device if loader is not None else None, verify=verify)
         except CacheError:
             pass  # stale or damaged cache: fall through to the CSV, then rewrite it
     data = (loader if loader is not None else _default_loader()).load_file(csv_filename)
-    save_trial(data, cpath, source=stamp)
+    try:
+        save_trial(data, cpath, source=stamp)
+    except OSError:
+        pass  # the cache is an optimisation; the data is what was asked for
     return data

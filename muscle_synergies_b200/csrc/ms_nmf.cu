@@ -45,6 +45,20 @@ __device__ __forceinline__ float ms_block_sum(float v, float* s_red) {
     return t;
 }
 
+// the same in double: the stop test compares residuals that differ in the sixth digit (tol = 1e-6 is the reference's
+// default, analysis.py:718-719); float sums over n*m terms carry roundoff of that order
+__device__ __forceinline__ double ms_block_sum_d(double v, float* s_red) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double* s_d = reinterpret_cast<double*>(s_red);
+    __syncthreads();
+    if (lane == 0) s_d[warp] = v;
+    __syncthreads();
+    double t = 0.0;
+    for (int w = 0; w < (int)(blockDim.x >> 5); w++) t += s_d[w];
+    return t;
+}
+
 // ---------------------------------------------------------------------------------------------------
 // resident regime
 // ---------------------------------------------------------------------------------------------------
@@ -124,7 +138,7 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
 
     // sum over the rows this thread owns of |x_i - w_i H|^2
     auto residual_sq = [&]() {
-        float acc = 0.f;
+        double acc = 0.0;
         for (int i = tid; i < n; i += NMF_THREADS) {
             float w[KP];
 #pragma unroll
@@ -142,10 +156,10 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
                     r = fmaf(-w[4 * q + 2], h.z, r);
                     r = fmaf(-w[4 * q + 3], h.w, r);
                 }
-                acc = fmaf(r, r, acc);
+                acc += (double)r * (double)r;
             }
         }
-        return ms_block_sum(acc, s_red);
+        return ms_block_sum_d(acc, s_red);
     };
     auto compute_hht = [&]() {
         for (int e = tid; e < K * K; e += NMF_THREADS) {
@@ -165,9 +179,9 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
         }
     };
 
-    float err0 = 0.f, prev = 0.f;
+    double err0 = 0.0, prev = 0.0;
     if (A.tol > 0.f) {
-        err0 = sqrtf(residual_sq());
+        err0 = sqrt(residual_sq());
         prev = err0;
     }
     compute_hht();
@@ -307,8 +321,8 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
         compute_hht();
         __syncthreads();
         if (A.tol > 0.f && it % A.check_every == 0) {
-            const float err = sqrtf(residual_sq());
-            if ((prev - err) / err0 < A.tol) break;
+            const double err = sqrt(residual_sq());
+            if (err0 == 0.0 || (prev - err) / err0 < (double)A.tol) break;  // an exactly factorised X has converged
             prev = err;
         }
     }
@@ -317,7 +331,7 @@ __device__ __forceinline__ void ms_nmf_resident_body(const MsNmfArgs& A, float* 
     // ---- results: factors, ||X - W H||_F, variance accounted for (analysis.py:642-667)
     for (int i = tid; i < n * K; i += NMF_THREADS) A.Wp[i] = sW[(i / K) * WS + (i % K)];
     for (int i = tid; i < K * m; i += NMF_THREADS) A.Hp[i] = sH[(i / m) * MP + (i % m)];
-    const float res = residual_sq();
+    const float res = (float)residual_sq();
     float xx = 0.f;
     for (int i = tid; i < n * m; i += NMF_THREADS) {
         const float v = sX[(i / m) * XS + (i % m)];
@@ -736,7 +750,7 @@ __global__ void __launch_bounds__(128)
             if (iteration == 0) {
                 stt->err0 = stt->prev = err;
             } else if (tol > 0.f && iteration % check_every == 0) {
-                if ((stt->prev - err) / stt->err0 < tol) stt->done = 1;
+                if (stt->err0 == 0.f || (stt->prev - err) / stt->err0 < tol) stt->done = 1;  // exact factorisation: converged
                 stt->prev = err;
             }
         }

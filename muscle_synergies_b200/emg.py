@@ -37,6 +37,7 @@ def _channel_major(signal_df: pandas.DataFrame):
     return torch.from_numpy(arr).cuda()
 
 
+@nat.on_tensor_device
 def channel_means(x):
     """Mean of every row of a (channels, samples) float64 CUDA tensor."""
     torch = _torch()
@@ -47,6 +48,7 @@ def channel_means(x):
     return out
 
 
+@nat.on_tensor_device
 def rms_envelope(x, window: int, mean=None):
     """sqrt(convolve((x - mean)^2, ones(window)/window, "same")) per row of a (channels, samples) tensor."""
     torch = _torch()
@@ -77,6 +79,7 @@ def filter_coeffs(critical_freqs, sampling_frequency: int, order: int, filter_ty
     return design(order, cheby_param, critical_freqs, btype=band_type, output="sos", fs=sampling_frequency)
 
 
+@nat.on_tensor_device
 def sos_filter(x, sos: np.ndarray, zero_lag: bool = True, mean=None, rectify: bool = False):
     """scipy.signal.sosfiltfilt (zero_lag) or sosfilt along every row of a (channels, samples) float64
     CUDA tensor; with `mean` / `rectify` the input is |x - mean| (the linear envelope's rectifier, fused)."""
@@ -118,6 +121,7 @@ def sos_filter(x, sos: np.ndarray, zero_lag: bool = True, mean=None, rectify: bo
     return out
 
 
+@nat.on_tensor_device
 def time_normalize_windows(env, starts: Sequence[int], stops: Sequence[int], reduce_to: int, normalize: bool = True):
     """(n_windows, reduce_to, channels) float64 CUDA tensor from a (channels, samples) envelope."""
     torch = _torch()
@@ -207,8 +211,15 @@ def normalize(signal_df: pandas.DataFrame, inplace: bool = False) -> pandas.Data
 
 
 def time_normalize(signal_df: pandas.DataFrame, reduce_to: int, kind="linear", fill_value="extrapolate") -> pandas.DataFrame:
-    if kind != "linear":
-        raise NotImplementedError('the CUDA stage implements kind="linear" only')
+    if kind != "linear" or fill_value != "extrapolate":
+        # what the reference does for every kind: scipy.interpolate.interp1d (analysis.py:584-594); the CUDA kernel
+        # covers the linear case the pipeline uses
+        from scipy import interpolate
+
+        percent_domain = np.linspace(0, 1, signal_df.shape[0])
+        interp_func = interpolate.interp1d(percent_domain, signal_df, axis=0, copy=False, kind=kind, fill_value=fill_value)
+        desired_domain = np.linspace(0, 1, reduce_to)
+        return pandas.DataFrame(interp_func(desired_domain), index=desired_domain, columns=signal_df.columns)
     x = _channel_major(signal_df)
     out = time_normalize_windows(x, [0], [int(x.shape[1])], reduce_to, normalize=False)[0]
     return pandas.DataFrame(out.cpu().numpy(), index=np.linspace(0, 1, reduce_to), columns=signal_df.columns)

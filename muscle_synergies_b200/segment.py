@@ -91,6 +91,7 @@ class _TransitionSearch:
     `extra_words` int64 slots follow the results in the same buffer (`extra`), so that work queued
     behind the search can return its own small outputs in the same device->host copy."""
 
+    @nat.on_tensor_device
     def __init__(self, left_fz, right_fz, min_phase_size: int, num_segments: int, extra_words: int = 0):
         import torch
 
@@ -255,13 +256,19 @@ class Segmenter:
             self._phase_cuts[id(dev)] = (dev, self._finish_phase_cuts(dev, out, extra[i * _PLAN_WORDS : (i + 1) * _PLAN_WORDS]))
 
     def _queue_phase_cuts(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData):
+        import torch
+
+        with torch.cuda.device(dev.tensor.device):
+            return self._queue_phase_cuts_on_device(search, dev, slot, plate)
+
+    def _queue_phase_cuts_on_device(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData):
         """Plans (on the device) and gathers the 32 phase windows of `dev` behind the search."""
         import torch
 
         lib = nat.lib()
         src = dev.tensor
         n_ch, n_rows = int(src.shape[0]), int(src.shape[1])
-        same_section = type(dev._frame_tracker) is type(plate._frame_tracker)
+        same_section = dev._frame_tracker.per_frame == plate._frame_tracker.per_frame
         divisor = 1 if same_section else plate._frame_tracker.num_subframes
         meta = search.extra[slot * _PLAN_WORDS : (slot + 1) * _PLAN_WORDS]
         starts, stops, offsets = meta[:32], meta[32:64], meta[64:97]
@@ -384,6 +391,7 @@ class Segmenter:
         return cut_windows(device, [device.to_index(w) for w in windows])
 
 
+@nat.on_tensor_device
 def cut_windows(device: DeviceData, index_slices: Sequence[slice]):
     """Batched `df.iloc[a:b]` on the device-resident block of one DeviceData."""
     import torch

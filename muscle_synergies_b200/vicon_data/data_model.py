@@ -9,7 +9,6 @@ exceptions.  Differences, all additive:
   * `DeviceData.df` is built lazily from a pinned host copy of the block, which has the
     memory layout pandas itself ends up with for the reference (user_data.py:396).
 """
-from functools import lru_cache
 from typing import List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -217,144 +216,122 @@ class ViconNexusData:
         )
 
 
-class _SectionFrameTracker:
-    """(frame, subframe) <-> row index for one section (user_data.py:483-623)."""
+class FrameIndex:
+    """(frame, subframe) <-> row index of one CSV section (the contract of user_data.py:483-661).
 
-    def __init__(self, sampling_freq: SamplingFreq):
+    One class for both sections, described by two numbers: `per_frame`, the rows a frame occupies in this section
+    (the number of subframes for forces / EMG, 1 for trajectories, where every subframe of a frame is the same
+    row), and the frame count.  Frames count from 1, subframes from 0, rows from 0.  Scalars, slices and whole
+    batches go through the same array arithmetic and the same bounds test."""
+
+    def __init__(self, sampling_freq: SamplingFreq, per_frame_is_subframes: bool):
         self._sampling_freq = sampling_freq
-        self._num_subframes = None  # computed (and its integrality asserted) on first use, like the reference
+        self._dense = per_frame_is_subframes
+        self._times = None
 
+    # ---- geometry
     @property
     def num_frames(self) -> int:
         return self._sampling_freq.num_frames
 
     @property
     def num_subframes(self) -> int:
-        if self._num_subframes is None:
-            self._num_subframes = self._sampling_freq.num_subframes
-        return self._num_subframes
+        return self._sampling_freq.num_subframes
+
+    @property
+    def per_frame(self) -> int:
+        return self.num_subframes if self._dense else 1
 
     @property
     def sampling_frequency(self) -> int:
-        raise NotImplementedError
+        return self._sampling_freq.freq_forces_emg if self._dense else self._sampling_freq.freq_traj
 
     @property
     def final_index(self) -> int:
-        raise NotImplementedError
+        return self.num_frames * self.per_frame - 1
 
-    def _to_index(self, framesubfr: FrameSubfr) -> int:
-        raise NotImplementedError
+    # ---- bounds: the reference's messages (user_data.py:575-597), first offender in argument order
+    def _check_rows(self, rows: np.ndarray, given):
+        bad = np.flatnonzero((rows < 0) | (rows > self.final_index) | (rows != np.floor(rows)))
+        if bad.size:
+            raise IndexError(f"index {given[int(bad[0])]} out of bounds (max is self.final_index)")
 
-    def _to_framesubfr(self, index: int) -> FrameSubfr:
-        raise NotImplementedError
+    def _check_pairs(self, frames: np.ndarray, subs: np.ndarray, given):
+        bad_f = (frames < 1) | (frames > self.num_frames) | (frames != np.floor(frames))
+        bad_s = (subs < 0) | (subs >= self.num_subframes) | (subs != np.floor(subs))
+        bad = np.flatnonzero(bad_f | bad_s)
+        if bad.size:
+            i = int(bad[0])
+            if bad_f[i]:
+                raise IndexError(f"frame {given[i][0]} is out of bounds")
+            raise IndexError(f"subframe {given[i][1]} out of range")
 
-    def to_index(self, frame, subframe):
-        if subframe is None:
-            if isinstance(frame, slice):
-                self._validate_slice(frame, self._validate_framesubfr_args)
-                return self._map_slice(frame, self._to_index)
-            frame, subframe = frame
-            return self._to_index((frame, subframe))
-        self._validate_framesubfr_args((frame, subframe))
-        return self._to_index((frame, subframe))
+    # ---- conversions on arrays
+    def _rows_of(self, frames: np.ndarray, subs: np.ndarray) -> np.ndarray:
+        return (frames - 1) * self.per_frame + (subs if self._dense else 0)
+
+    def _pairs_of(self, rows: np.ndarray):
+        return rows // self.per_frame + 1, (rows % self.per_frame if self._dense else np.zeros_like(rows))
+
+    @staticmethod
+    def _slice_parts(slice_):
+        """The parts of a slice in the order the reference validates them: stop, then start and step if given."""
+        return [("stop", slice_.stop)] + [(k, v) for k, v in (("start", slice_.start), ("step", slice_.step)) if v is not None]
+
+    # ---- the reference's two methods
+    def to_index(self, frame, subframe=None):
+        if subframe is not None:
+            return self.to_index_many([(frame, subframe)])[0]
+        if not isinstance(frame, slice):
+            f, s = frame  # a pair given as one argument is converted unchecked, as in the reference (user_data.py:527-528)
+            return int(self._rows_of(np.asarray(f), np.asarray(s)))
+        parts = self._slice_parts(frame)
+        rows = dict(zip((k for k, _ in parts), self.to_index_many([v for _, v in parts])))
+        return slice(rows.get("start"), rows.get("stop"), rows.get("step"))
 
     def to_framesubfr(self, index):
-        if isinstance(index, slice):
-            self._validate_slice(index, self._validate_index_arg)
-            return self._map_slice(index, self._to_framesubfr)
-        self._validate_index_arg(index)
-        return self._to_framesubfr(index)
+        if not isinstance(index, slice):
+            return self.to_framesubfr_many([index])[0]
+        parts = self._slice_parts(index)
+        pairs = dict(zip((k for k, _ in parts), self.to_framesubfr_many([v for _, v in parts])))
+        return slice(pairs.get("start"), pairs.get("stop"), pairs.get("step"))
 
-    # ---- batch forms (extension): same checks and results as a loop over the scalar methods, without
-    # the per-call overhead - the windowing stage converts 64 bounds per trial on its critical path
-    def to_framesubfr_many(self, indices: Sequence[int]) -> List[FrameSubfr]:
-        final = self.final_index
-        for index in indices:
-            if not 0 <= index <= final or index != int(index):
-                self._validate_index_arg(index)  # raises the scalar method's IndexError
-        return [self._to_framesubfr(index) for index in indices]
-
+    # ---- batches (extension: the windowing stage converts 64 bounds per trial)
     def to_index_many(self, pairs: Sequence[FrameSubfr]) -> List[int]:
-        frames, subs = self.num_frames, self.num_subframes
-        out = []
-        for pair in pairs:
-            frame, sub = pair
-            if not (1 <= frame <= frames and 0 <= sub < subs) or frame != int(frame) or sub != int(sub):
-                self._validate_framesubfr_args(pair)
-            out.append(self._to_index(pair))
-        return out
+        given = [tuple(p) for p in pairs]
+        if not given:
+            return []
+        arr = np.asarray(given)
+        self._check_pairs(arr[:, 0], arr[:, 1], given)
+        return [int(r) for r in self._rows_of(arr[:, 0].astype(np.int64), arr[:, 1].astype(np.int64))]
 
-    def _validate_index_arg(self, index: int):
-        if index not in range(self.final_index + 1):
-            raise IndexError(f"index {index} out of bounds (max is self.final_index)")
-
-    def _validate_framesubfr_args(self, framesubfr: FrameSubfr):
-        frame, subframe = framesubfr
-        if frame not in range(1, self.num_frames + 1):
-            raise IndexError(f"frame {frame} is out of bounds")
-        if subframe not in range(self.num_subframes):
-            raise IndexError(f"subframe {subframe} out of range")
-
-    @staticmethod
-    def _validate_slice(slice_, validate):
-        validate(slice_.stop)
-        for arg in {slice_.start, slice_.step}:
-            if arg is not None:
-                validate(arg)
-
-    @staticmethod
-    def _map_slice(slice_, func):
-        def maybe(arg):
-            return None if arg is None else func(arg)
-
-        return slice(maybe(slice_.start), maybe(slice_.stop), maybe(slice_.step))
+    def to_framesubfr_many(self, indices: Sequence[int]) -> List[FrameSubfr]:
+        given = list(indices)
+        if not given:
+            return []
+        rows = np.asarray(given)
+        self._check_rows(rows, given)
+        frames, subs = self._pairs_of(rows.astype(np.int64))
+        return [(int(f), int(s)) for f, s in zip(frames, subs)]
 
     def time_seq(self) -> pd.Series:
-        return self._time_seq(self.sampling_frequency, self.final_index + 1)
-
-    @staticmethod
-    @lru_cache(maxsize=2)
-    def _time_seq(sampling_frequency: int, num_measurements: int) -> pd.Series:
-        period = 1 / sampling_frequency
-        return pd.Series(period * np.arange(1, num_measurements + 1, 1))
+        """Sample k (from 0) is at (k + 1) / f (user_data.py:605-608)."""
+        if self._times is None or len(self._times) != self.final_index + 1:
+            self._times = pd.Series(np.arange(1, self.final_index + 2, 1) * (1 / self.sampling_frequency))
+        return self._times
 
 
-class ForcesEMGFrameTracker(_SectionFrameTracker):
-    _final_index = None
-
-    @property
-    def sampling_frequency(self) -> int:
-        return self._sampling_freq.freq_forces_emg
-
-    def _to_index(self, framesubfr):
-        frame, subframe = framesubfr
-        return (frame - 1) * self.num_subframes + subframe
-
-    def _to_framesubfr(self, index):
-        return (index // self.num_subframes) + 1, index % self.num_subframes
-
-    @property
-    def final_index(self) -> int:
-        if self._final_index is None:
-            self._final_index = self.num_frames * self.num_subframes - 1
-        return self._final_index
+def ForcesEMGFrameTracker(sampling_freq: SamplingFreq) -> FrameIndex:
+    """The Devices section: `num_subframes` rows per frame (user_data.py:626-642)."""
+    return FrameIndex(sampling_freq, per_frame_is_subframes=True)
 
 
-class TrajFrameTracker(_SectionFrameTracker):
-    @property
-    def sampling_frequency(self) -> int:
-        return self._sampling_freq.freq_traj
+def TrajFrameTracker(sampling_freq: SamplingFreq) -> FrameIndex:
+    """The Trajectories section: one row per frame, whatever the subframe (user_data.py:645-661)."""
+    return FrameIndex(sampling_freq, per_frame_is_subframes=False)
 
-    def _to_index(self, framesubfr):
-        frame, _subframe = framesubfr
-        return frame - 1
 
-    def _to_framesubfr(self, index):
-        return index + 1, 0
-
-    @property
-    def final_index(self) -> int:
-        return self.num_frames - 1
+_SectionFrameTracker = FrameIndex
 
 
 class DeviceData:

@@ -865,7 +865,8 @@ def _raise_device_error(src: _Source, plan: _Plan, key: int, name: str, ws):
         raise wrap_error(row_index + 1, name, exc) from exc
     if kind == nat.MS_ERR_KIND_NON_ASCII:
         raise NotImplementedError(
-            f"{name}: line {row_index + 1} has a non-ASCII numeric field; CPython accepts it but the CUDA loader does not"
+            f"{name}: line {row_index + 1} has a numeric field of more than 128 characters with non-ASCII ones among them; "
+            "CPython accepts it but the CUDA loader does not"
         )
     raise AssertionError(f"{name}: device rejected a field on line {row_index + 1} that float() accepts")
 

@@ -59,9 +59,42 @@ def test_known_answer_table(harness):
         agree(harness, text.encode("latin1"))
 
 
-def test_non_ascii_is_flagged_not_parsed(harness):
-    for s in (" 1".encode(), "1 ".encode(), "١".encode(), b"1\xff"):
-        assert dev_parse(harness, s)[0] == 2
+def py_parse_text(text: str):
+    try:
+        return 0, struct.unpack("<Q", struct.pack("<d", float(text)))[0]
+    except ValueError:
+        return 1, 0
+
+
+def test_non_ascii_fields_follow_float_of_str(harness):
+    """float(str) maps Unicode decimal digits and spaces to ASCII first (float("\uff11\uff12")
+    is 12.0); bytes that are not UTF-8 cannot come out of open(filename) at all and are flagged."""
+    import unicodedata
+
+    rnd = random.Random(21)
+    zeros = [cp for cp in range(0x80, 0x110000) if unicodedata.decimal(chr(cp), None) == 0]
+    spaces = [chr(cp) for cp in range(0x80, 0x3100) if chr(cp).isspace()]
+    cases = ["\uff11\uff12", "\u0663", "\u00a01.5\u2003", "1\u00e9", "x\uff11", "\uff11e\uff12", "\u0967\u0968\u0969.\u096a", "\u2028",
+             "1\u00a02", "-\u0660.\u0665", "\U0001d7ce\U0001d7cf", "nan\u3000", "\u221e", "1\x7f"]
+    for _ in range(3000):
+        parts = []
+        for _ in range(rnd.randrange(1, 8)):
+            r = rnd.random()
+            if r < 0.45:
+                parts.append(chr(rnd.choice(zeros) + rnd.randrange(10)))
+            elif r < 0.7:
+                parts.append(rnd.choice("0123456789.-+e_"))
+            elif r < 0.85:
+                parts.append(rnd.choice(spaces))
+            else:
+                parts.append(chr(rnd.choice([0xe9, 0x3b1, 0x4e00, 0x1f600, 0x7f, 0xb2, 0x2160])))  # letters, superscript two, roman one
+        cases.append("".join(parts))
+    for text in cases:
+        raw = text.encode("utf-8")
+        got, want = dev_parse(harness, raw), py_parse_text(text)
+        assert got[0] == want[0] and (got[0] != 0 or got[1] == want[1]), (text, got, want)
+    for raw in (b"1\xff", b"\xc0\xb1", b"\xed\xa0\x80", b"\xf4\x90\x80\x80", b"\xe0\x80"):  # stray, overlong, surrogate, > U+10FFFF, cut short
+        assert dev_parse(harness, raw)[0] == 2, raw
 
 
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
