@@ -47,8 +47,10 @@ def test_dataframe_level_functions(emg):
         assert list(got.columns) == list(df.columns) and np.allclose(got.index, np.linspace(0, 1, r))
     inplace = df.copy()
     assert emg.zero_center(inplace, inplace=True) is inplace
-    with pytest.raises(NotImplementedError):
-        emg.time_normalize(df, 10, kind="cubic")
+    from scipy import interpolate
+
+    cubic = interpolate.interp1d(np.linspace(0, 1, len(df)), df, axis=0, kind="cubic", fill_value="extrapolate")(np.linspace(0, 1, 10))
+    assert np.array_equal(emg.time_normalize(df, 10, kind="cubic").to_numpy(), cubic)  # other kinds: scipy, as in the reference
 
 
 def test_envelope_windows_on_a_segmented_trial(emg):

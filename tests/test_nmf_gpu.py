@@ -111,8 +111,12 @@ def test_find_synergies_api(analysis):
         analysis.find_synergies(df, 3, 17, solver="mu", init="random")
     with pytest.raises(ValueError):
         analysis.find_synergies(df.iloc[:0], 3, solver="mu", init="random")
-    with pytest.raises(NotImplementedError):
-        analysis.find_synergies(df, 3)  # sklearn's default solver="cd" is not what this stage implements
+    import warnings
+
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        default = analysis.find_synergies(df, 3, max_iter=300)  # sklearn's default solver="cd": forwarded, as in the reference
+    assert type(default.model).__name__ == "NMF" and default.components.shape == (3, df.shape[1])
 
 
 def test_other_shapes(analysis):
