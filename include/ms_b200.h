@@ -42,7 +42,7 @@ extern "C" {
 #ifndef MS_TILE_BYTES
 #define MS_TILE_BYTES 49152     /* bytes of CSV owned by one thread block */
 #endif
-#define MS_MAX_ROW_BYTES 8192   /* longest supported CSV row (overhang read past a tile) */
+#define MS_MAX_ROW_BYTES 8192   /* longest CSV row of the tiled kernels (overhang staged past a tile); ms_parse_long beyond */
 #define MS_MAX_BLANK_ROWS 8     /* blank rows reported by ms_scan (first ones, file order) */
 #define MS_MAX_SECTIONS 4
 
@@ -80,7 +80,7 @@ typedef struct ms_section {
 #define MS_ERR_NONE 0xFFFFFFFFFFFFFFFFull
 #define MS_ERR_KIND_BAD_FLOAT 1u   /* float(field) raises ValueError */
 #define MS_ERR_KIND_NON_ASCII 2u   /* byte >= 0x80 in a numeric field: unsupported on device */
-#define MS_ERR_KIND_ROW_TOO_LONG 3u /* a row exceeds MS_MAX_ROW_BYTES */
+#define MS_ERR_KIND_ROW_TOO_LONG 3u /* a row exceeds MS_MAX_ROW_BYTES: parse the buffer with ms_parse_long */
 
 /* ---- loader ------------------------------------------------------------------------- */
 
@@ -113,6 +113,14 @@ int ms_scan_quoted(const uint8_t* d_bytes, int64_t n_bytes, void* d_workspace, i
  * d_status: one uint64 in device memory (see MS_ERR_*). */
 int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
              int32_t n_sections, uint64_t* d_status, void* stream);
+
+/* Rows of any length: ms_parse reports MS_ERR_KIND_ROW_TOO_LONG for a buffer with a row it cannot stage
+ * (> MS_MAX_ROW_BYTES); this entry point parses such a buffer instead - one thread per row, straight from global
+ * memory, same outputs and status word.  Needs the workspace of ms_scan (or ms_scan_quoted) for the same buffer,
+ * its summary's n_terminators, and d_rows: ms_parse_long_workspace_bytes(n_terminators) bytes of device scratch. */
+int64_t ms_parse_long_workspace_bytes(int64_t n_terminators);
+int ms_parse_long(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
+                  int32_t n_sections, int64_t n_terminators, void* d_rows, uint64_t* d_status, void* stream);
 
 /* ---- loader, single pass ----------------------------------------------------------------- */
 

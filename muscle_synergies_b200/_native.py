@@ -119,6 +119,8 @@ def _declare(L):
         "ms_nmf_stream_workspace_bytes": (i64, [i32, i32]),
         "ms_nmf_mu_stream": (ctypes.c_int, [vp, i64, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, vp, i32,
                                             ctypes.c_float, i32, vp, vp, vp, vp, vp]),
+        "ms_parse_long_workspace_bytes": (i64, [i64]),
+        "ms_parse_long": (ctypes.c_int, [vp, i64, vp, ctypes.POINTER(Section), i32, i64, vp, vp, vp]),
         "ms_load_workspace_bytes": (i64, [i64, i32]),
         "ms_load_fused": (ctypes.c_int, [vp, i64, ctypes.POINTER(LoadPlan), vp, i64, vp, vp, vp]),
         "ms_copy_rows_to_host": (ctypes.c_int, [vp, i64, vp, i64, i64, i64, vp]),

@@ -960,3 +960,154 @@ extern "C" int ms_parse(const uint8_t* d_bytes, int64_t n_bytes, const void* d_w
     MS_CUDA_CHECK(cudaGetLastError());
     return MS_OK;
 }
+
+// ===================================================================================================
+// rows of any length
+// ===================================================================================================
+// The tiled kernels stage a tile and MS_MAX_ROW_BYTES beyond it; a file with a longer row (a Trajectories section of
+// more than ~300 markers, or 800-digit numbers) is parsed by this pair instead: exact, unhurried, straight from
+// global memory.  ms_row_index_kernel turns the scan's terminator masks into the byte offset of every row;
+// ms_parse_rows_kernel gives every data row to one thread, which walks its fields by the scan's comma masks (so a
+// quote-aware scan is honoured) and parses each with the general parser.  Same outputs and status word as ms_parse.
+__global__ void __launch_bounds__(256)
+    ms_row_index_kernel(const uint32_t* __restrict__ masks, long long n, const unsigned long long* __restrict__ term_prefix,
+                        long long* __restrict__ row_start) {
+    __shared__ int s_warp[8];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const long long tile = blockIdx.x;
+    const long long seg0 = tile * (MS_TILE_BYTES / 16), n_seg = (n + 15) >> 4;
+    constexpr int PER = MS_TILE_BYTES / 16 / 256;  // mask words per thread, consecutive
+    uint32_t term[PER];
+    int mine = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        const long long sa = seg0 + (long long)tid * PER + k;
+        term[k] = sa < n_seg ? (masks[sa] & 0xffffu) : 0u;
+        mine += __popc(term[k]);
+    }
+    int inc = mine;
+#pragma unroll
+    for (int d = 1; d < 32; d <<= 1) {
+        const int o = __shfl_up_sync(0xffffffffu, inc, d);
+        if (lane >= d) inc += o;
+    }
+    if (lane == 31) s_warp[warp] = inc;
+    __syncthreads();
+    int before = inc - mine;
+    for (int w = 0; w < warp; w++) before += s_warp[w];
+    long long j = (long long)term_prefix[tile] + before;  // ordinal of my first terminator in the file
+    if (tile == 0 && tid == 0) row_start[0] = 0;
+#pragma unroll
+    for (int k = 0; k < PER; k++) {
+        uint32_t t = term[k];
+        while (t) {
+            const int b = __ffs(t) - 1;
+            t &= t - 1u;
+            row_start[++j] = ((seg0 + (long long)tid * PER + k) << 4) + b + 1;  // row j starts after terminator j - 1
+        }
+    }
+}
+
+// float() of the csv field src[s, e) (quotes handled as csv.reader's excel dialect does, load_csv.py:30)
+__device__ int ms_parse_span(const uint8_t* __restrict__ src, long long s, long long e, uint64_t* bits) {
+    *bits = MS_NAN_BITS;
+    if (s >= e) return MS_PARSE_OK;  // empty: None -> NaN
+    if (src[s] != '"') return ms_parse_field(src + s, src + e, bits);
+    uint8_t buf[MS_QUOTED_MAX];
+    int n = 0;
+    bool open = true;
+    for (long long q = s + 1; q < e; q++) {
+        const unsigned c = src[q];
+        if (open && c == '"') {
+            if (q + 1 < e && src[q + 1] == '"')
+                q++;  // "" inside quotes: one literal quote
+            else {
+                open = false;
+                continue;
+            }
+        }
+        if (n >= MS_QUOTED_MAX) return MS_PARSE_BAD;
+        buf[n++] = (uint8_t)c;
+    }
+    if (n == 0) return MS_PARSE_OK;
+    return ms_parse_field(buf, buf + n, bits);
+}
+
+__global__ void __launch_bounds__(128)
+    ms_parse_rows_kernel(const uint8_t* __restrict__ src, long long n, const uint32_t* __restrict__ masks,
+                         const long long* __restrict__ row_start, long long n_terminators, const MsSectionsArg secs,
+                         unsigned long long* __restrict__ status) {
+    const long long n_rows = n_terminators + ((n_terminators == 0 ? n > 0 : row_start[n_terminators] < n) ? 1 : 0);
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n_rows; r += (long long)gridDim.x * blockDim.x) {
+        int si = -1;
+        for (int i = 0; i < secs.n; i++)
+            if (r >= secs.s[i].row_begin && r < secs.s[i].row_end) si = i;
+        if (si < 0) continue;
+        const int ncols = secs.s[si].num_cols, n_keep = secs.s[si].n_keep;
+        double* const out = secs.s[si].d_out + (r - secs.s[si].row_begin);
+        const long long stride = secs.s[si].stride;
+        long long p = row_start[r];
+        // one past the row's last content byte: before its terminator ("\n", "\r\n" or "\r"), or the end of the file
+        long long end = r < n_terminators ? row_start[r + 1] - 1 : n;
+        if (r < n_terminators && src[end] == '\n' && end > p && src[end - 1] == '\r') end--;
+        bool done = false;
+        for (int c = 0; c < ncols; c++) {
+            uint64_t bits = MS_NAN_BITS;
+            if (!done) {
+                // the field ends at the next comma the scan recorded, or with the row
+                long long e = end;
+                for (long long w = p >> 4; (w << 4) < end; w++) {
+                    uint32_t cm = masks[w] >> 16;
+                    if (w == (p >> 4)) cm &= ~((1u << (p & 15)) - 1u);
+                    if (cm) {
+                        const long long at = (w << 4) + __ffs(cm) - 1;
+                        if (at < end) e = at;
+                        break;
+                    }
+                }
+                const int st = ms_parse_span(src, p, e, &bits);
+                if (st != MS_PARSE_OK) {
+                    bits = MS_NAN_BITS;
+                    atomicMin(status, ((unsigned long long)p << 3) |
+                                          (st == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+                }
+                done = e >= end;
+                p = e + 1;
+            }
+            const int ch = c - 2;
+            if (ch >= 0 && ch < n_keep) out[(long long)ch * stride] = ms_bits_to_double(bits);
+        }
+    }
+}
+
+extern "C" int64_t ms_parse_long_workspace_bytes(int64_t n_terminators) { return (n_terminators + 2) * 8; }
+
+extern "C" int ms_parse_long(const uint8_t* d_bytes, int64_t n_bytes, const void* d_workspace, const ms_section* h_sections,
+                             int32_t n_sections, int64_t n_terminators, void* d_rows, uint64_t* d_status, void* stream) {
+    if (!d_bytes || !d_workspace || !d_status || !d_rows || n_bytes < 0 || n_terminators < 0) return MS_E_INVALID;
+    if (n_sections < 0 || n_sections > MS_MAX_SECTIONS || (n_sections > 0 && !h_sections)) return MS_E_INVALID;
+    cudaStream_t st = (cudaStream_t)stream;
+    MS_CUDA_CHECK(cudaMemsetAsync(d_status, 0xFF, sizeof(uint64_t), st));
+    MsSectionsArg arg;
+    memset(&arg, 0, sizeof arg);
+    for (int i = 0; i < n_sections; i++) {
+        const ms_section& s = h_sections[i];
+        if (s.row_end <= s.row_begin || s.num_cols <= 0) continue;
+        if (!s.d_out && s.n_keep > 0) return MS_E_INVALID;
+        if (s.stride < s.row_end - s.row_begin || s.n_keep < 0 || s.n_keep > s.num_cols) return MS_E_INVALID;
+        arg.s[arg.n++] = s;
+    }
+    const int64_t n_tiles = ms_num_tiles(n_bytes);
+    if (n_tiles == 0 || arg.n == 0) return MS_OK;
+    MsWorkspaceView v = ms_view(const_cast<void*>(d_workspace), n_tiles, n_bytes);
+    ms_row_index_kernel<<<(unsigned)n_tiles, 256, 0, st>>>(v.masks, n_bytes, v.term_prefix, (long long*)d_rows);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    const int64_t n_rows = n_terminators + 1;
+    const unsigned blocks = (unsigned)((n_rows + 127) / 128 < 148 * 16 ? (n_rows + 127) / 128 : 148 * 16);
+    ms_parse_rows_kernel<<<blocks, 128, 0, st>>>(d_bytes, n_bytes, v.masks, (const long long*)d_rows, n_terminators, arg,
+                                                 (unsigned long long*)d_status);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}

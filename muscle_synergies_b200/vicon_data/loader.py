@@ -159,14 +159,18 @@ class _Source:
         bits = torch.zeros((), dtype=torch.int64, device=masks.device)
         for k in range(16):  # popcount of the terminator bits before the segment of `pos`
             bits += ((term[:seg] >> k) & 1).sum()
-        lo = max(0, seg - nat.MS_MAX_ROW_BYTES // 16 - 2)
-        hi = min(n_seg, seg + nat.MS_MAX_ROW_BYTES // 16 + 2)
-        window = term[lo:hi].cpu().numpy().astype(np.int64)
-        ends = [16 * (lo + i) + b for i, m in enumerate(window) for b in range(16) if (m >> b) & 1]
-        before = [e for e in ends if e < pos]
-        after = [e for e in ends if e >= pos]
+        reach = nat.MS_MAX_ROW_BYTES // 16 + 2
+        while True:  # widen until the row's two ends are in the window (rows may be longer than a tile's overhang)
+            lo, hi = max(0, seg - reach), min(n_seg, seg + reach)
+            window = term[lo:hi].cpu().numpy().astype(np.int64)
+            ends = [16 * (lo + i) + b for i, m in enumerate(window) if m for b in range(16) if (m >> b) & 1]
+            before = [e for e in ends if e < pos]
+            after = [e for e in ends if e >= pos]
+            if (before or lo == 0) and (after or hi == n_seg):
+                break
+            reach *= 8
         row = int(bits.item()) + sum(1 for e in before if e >= 16 * seg)
-        start = before[-1] + 1 if before else (0 if lo == 0 else 16 * lo)
+        start = before[-1] + 1 if before else 0
         stop = after[0] + 1 if after else self.n
         return row, start, stop
 
@@ -524,9 +528,19 @@ class ViconLoader:
         except (TypeError, ValueError, KeyError) as exc:
             build_error = exc
 
+        n_terminators = int(summary.n_terminators)
+
         def check():
             copied.synchronize()
             key = int(h_status.item()) & 0xFFFFFFFFFFFFFFFF
+            if key != nat.MS_ERR_NONE and key & 7 == nat.MS_ERR_KIND_ROW_TOO_LONG:
+                # a row the tiled kernel cannot stage: the whole buffer again with one thread per row (ms_parse_long)
+                with self.torch.cuda.device(self.device), self._on_stream(stream):
+                    d_rows = torch.empty(int(self.lib.ms_parse_long_workspace_bytes(n_terminators)), dtype=torch.uint8,
+                                         device=self.device)
+                    nat.check(self.lib.ms_parse_long(src.d_bytes.data_ptr(), src.n, ws.data_ptr(), sections, n_sec,
+                                                     n_terminators, d_rows.data_ptr(), d_status.data_ptr(), sptr), "ms_parse_long")
+                    key = int(d_status.cpu().item()) & 0xFFFFFFFFFFFFFFFF
             if key != nat.MS_ERR_NONE:
                 _raise_device_error(src, plan, key, name, ws)
             if plan.deferred_error is not None:
