@@ -22,7 +22,9 @@
  *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
  *   - every entry point returns 0 on success or a negative MS_E_* code; kernels are
  *     enqueued asynchronously on `stream` unless stated otherwise.
- *   - re-entrant: no global mutable state; one workspace per concurrent call.
+ *   - re-entrant: one workspace per concurrent call.  The only process-wide state is bookkeeping that no result
+ *     depends on: an atomic count of kernel launches (ms_launch_count) and, per calling thread, the text of the
+ *     last CUDA failure (ms_last_cuda_error).
  */
 #ifndef MS_B200_H
 #define MS_B200_H
@@ -154,9 +156,11 @@ typedef struct ms_load_plan {
     int64_t arena_elems;  /* doubles in the arena */
     int64_t cap_rows[2];  /* row capacity (= channel stride) of each section's block; cap_rows[1] == 0: the
                              second block takes what the first one leaves of the arena */
-    int32_t tile_bytes;   /* CSV bytes per thread block, a multiple of 16 in [4096, MS_TILE_BYTES]; 0 = MS_TILE_BYTES.
-                             Fewest idle lanes when a tile holds just under a multiple of 32 rows. */
-    int32_t reserved;
+    int32_t tile_bytes;   /* CSV bytes per thread block, a multiple of 16, at least 4096; 0 = the largest that fits
+                             shared memory next to the overhang (MS_TILE_BYTES at most when overhang_bytes is 0) */
+    int32_t overhang_bytes; /* bytes staged past a tile to finish its last row = the longest row this launch can
+                             take (longer: MS_LOAD_ROW_TOO_LONG); a multiple of 16 in [512, MS_MAX_ROW_BYTES];
+                             0 = MS_MAX_ROW_BYTES.  Tile + overhang share 56 KiB: short rows leave more to the tile. */
 } ms_load_plan;
 
 /* Written to DEVICE memory; copy it back after the stream is done. */
@@ -195,6 +199,23 @@ int64_t ms_transitions_workspace_bytes(int64_t n);
 int ms_find_transitions(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
                         int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded,
                         int32_t* d_n_found, void* stream);
+
+/* ms_find_transitions and, in the same launch, ms_plan_phase_windows for up to MS_MAX_WINDOW_PLANS devices (the
+ * block that finishes the bitmaps last runs the search and the plans): what Segmenter(data) needs from the GPU is
+ * then one launch, and the gathers of ms_cut_windows can be queued right behind it. */
+#define MS_MAX_WINDOW_PLANS 4
+typedef struct ms_window_plan {
+    int64_t divisor;     /* 1 for force plates / EMG, num_subframes for trajectory markers */
+    int64_t n_rows;      /* rows of the device's block */
+    int32_t n_channels;
+    int32_t cycles;      /* 0: the 32 phase windows, else the 8 cycle windows */
+    int64_t* d_starts;   /* outputs, as ms_plan_phase_windows */
+    int64_t* d_stops;
+    int64_t* d_offsets;
+} ms_window_plan;
+int ms_segment_trial(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
+                     int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded, int32_t* d_n_found,
+                     const ms_window_plan* h_plans, int32_t n_plans, void* stream);
 
 /* Row ranges of the 32 phase windows (cycles == 0; order: trecho, cycle, phase) or the 8 cycle windows
  * (cycles != 0) of one device, from transitions still in device memory (the output of

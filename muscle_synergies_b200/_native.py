@@ -63,7 +63,7 @@ class LoadPlan(ctypes.Structure):
         ("arena_elems", ctypes.c_int64),
         ("cap_rows", ctypes.c_int64 * 2),
         ("tile_bytes", ctypes.c_int32),
-        ("reserved", ctypes.c_int32),
+        ("overhang_bytes", ctypes.c_int32),
     ]
 
 
@@ -87,6 +87,21 @@ class LoadResult(ctypes.Structure):
     ]
 
 
+class WindowPlan(ctypes.Structure):
+    _fields_ = [
+        ("divisor", ctypes.c_int64),
+        ("n_rows", ctypes.c_int64),
+        ("n_channels", ctypes.c_int32),
+        ("cycles", ctypes.c_int32),
+        ("d_starts", ctypes.c_void_p),
+        ("d_stops", ctypes.c_void_p),
+        ("d_offsets", ctypes.c_void_p),
+    ]
+
+
+MS_MAX_WINDOW_PLANS = 4
+
+
 class NativeError(RuntimeError):
     pass
 
@@ -105,6 +120,7 @@ def _declare(L):
         "ms_parse": (ctypes.c_int, [vp, i64, vp, ctypes.POINTER(Section), i32, vp, vp]),
         "ms_transitions_workspace_bytes": (i64, [i64]),
         "ms_find_transitions": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, vp]),
+        "ms_segment_trial": (ctypes.c_int, [vp, vp, i64, i32, i32, vp, vp, vp, vp, ctypes.POINTER(WindowPlan), i32, vp]),
         "ms_cut_windows": (ctypes.c_int, [vp, i64, i32, vp, vp, vp, i32, vp, i64, vp]),
         "ms_plan_phase_windows": (ctypes.c_int, [vp, vp, i32, i32, i64, i64, i32, vp, vp, vp, vp]),
         "ms_channel_means": (ctypes.c_int, [vp, i64, i32, i64, vp, vp]),

@@ -131,7 +131,7 @@ struct MsFusedArgs {
     long long arena_elems;
     long long cap_rows[2];
     int tile_bytes;
-    int region_bytes;  // tile_bytes + MS_MAX_ROW_BYTES
+    int region_bytes;  // tile_bytes + the overhang staged past the tile
     long long n_tiles;
 };
 
@@ -840,17 +840,26 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
 // ===================================================================================================
 // C ABI
 // ===================================================================================================
-static int ms_fused_tile_bytes(int32_t tile_bytes) {
-    if (tile_bytes <= 0) return FUSED_MAX_TILE;
+// bytes a tile stages past its end (the longest row it can finish), and the tile size that then fits shared memory
+static int ms_fused_overhang(int32_t overhang_bytes) {
+    if (overhang_bytes <= 0) return MS_MAX_ROW_BYTES;
+    int o = (overhang_bytes + 15) / 16 * 16;
+    if (o < 512) o = 512;
+    if (o > MS_MAX_ROW_BYTES) o = MS_MAX_ROW_BYTES;
+    return o;
+}
+static int ms_fused_tile_bytes(int32_t tile_bytes, int overhang) {
+    const int largest = FUSED_MAX_REGION - overhang;
+    if (tile_bytes <= 0) return largest < FUSED_MAX_TILE ? largest : FUSED_MAX_TILE;
     int t = tile_bytes / 16 * 16;
     if (t < 4096) t = 4096;
-    if (t > FUSED_MAX_TILE) t = FUSED_MAX_TILE;
+    if (t > largest) t = largest;
     return t;
 }
 
 extern "C" int64_t ms_load_workspace_bytes(int64_t n_bytes, int32_t tile_bytes) {
-    const int t = ms_fused_tile_bytes(tile_bytes);
-    const int64_t n_tiles = n_bytes <= 0 ? 0 : (n_bytes + t - 1) / t;
+    (void)tile_bytes;  // sized for the smallest tile: a look-back word per tile is cheap, and any plan then fits
+    const int64_t n_tiles = n_bytes <= 0 ? 0 : (n_bytes + 4095) / 4096;
     return FUSED_LB_OFFSET + (n_tiles + 1) * 8;
 }
 
@@ -859,10 +868,11 @@ extern "C" int ms_load_fused(const uint8_t* d_bytes, int64_t n_bytes, const ms_l
     if (!d_bytes || !h_plan || !d_workspace || !d_result || !d_peek || n_bytes < 0) return MS_E_INVALID;
     if (((uintptr_t)d_bytes & 15) != 0 || ((uintptr_t)d_workspace & 15) != 0) return MS_E_INVALID;
     if (!h_plan->d_arena || h_plan->arena_elems < 0 || h_plan->cap_rows[0] <= 0 || h_plan->cap_rows[1] < 0) return MS_E_INVALID;
-    const int tile = ms_fused_tile_bytes(h_plan->tile_bytes);
-    const int64_t need = ms_load_workspace_bytes(n_bytes, tile);
-    if (workspace_bytes < need) return MS_E_WORKSPACE;
+    const int overhang = ms_fused_overhang(h_plan->overhang_bytes);
+    const int tile = ms_fused_tile_bytes(h_plan->tile_bytes, overhang);
+    if (workspace_bytes < ms_load_workspace_bytes(n_bytes, tile)) return MS_E_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
+    const int64_t need = FUSED_LB_OFFSET + ((n_bytes + tile - 1) / tile + 1) * 8;  // what this launch touches
     MS_CUDA_CHECK(cudaMemsetAsync(d_workspace, 0, (size_t)need, st));
     MS_CUDA_CHECK(cudaMemsetAsync(d_result, 0, sizeof(ms_load_result), st));
     MS_CUDA_CHECK(cudaMemsetAsync(&d_result->status, 0xFF, sizeof(uint64_t), st));
@@ -874,7 +884,7 @@ extern "C" int ms_load_fused(const uint8_t* d_bytes, int64_t n_bytes, const ms_l
     a.cap_rows[0] = h_plan->cap_rows[0];
     a.cap_rows[1] = h_plan->cap_rows[1];
     a.tile_bytes = tile;
-    a.region_bytes = tile + MS_MAX_ROW_BYTES;
+    a.region_bytes = tile + overhang;
     a.n_tiles = n_tiles;
     MS_CUDA_CHECK(cudaFuncSetAttribute(ms_load_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, FUSED_SMEM));
     ms_load_kernel<<<(unsigned)n_tiles, FUSED_THREADS, FUSED_SMEM, st>>>(d_bytes, n_bytes, (MsFusedWs*)d_workspace, a, d_result,

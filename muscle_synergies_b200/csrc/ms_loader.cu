@@ -1,15 +1,18 @@
-// Vicon Nexus CSV loader kernels for sm_100a.
+// Vicon Nexus CSV loader kernels for sm_100a: the two-pass path (the single-pass kernel is in ms_fused.cu).
 //
-//   ms_scan_kernel     pass 1, one CTA per 48 KiB tile: row terminators, quotes, blank rows
-//   ms_resolve_kernel  single CTA: terminator prefix per tile, blank rows that straddle
-//                      tiles, their csv row indices -> ms_scan_summary
-//   ms_parse_kernel    pass 2, one CTA per tile: (row, column) of every field by a block-wide
-//                      segmented scan over delimiter masks -> shared (row x column) table of
-//                      field offsets -> column-major sweep: correctly rounded decimal->double,
-//                      coalesced stores into channel-major float64 arrays
+//   ms_scan_kernel     pass 1, one CTA per 48 KiB tile: row terminators, quotes, blank rows; leaves the
+//                      terminator / comma masks of every 16-byte segment for pass 2
+//   ms_resolve_kernel  single CTA: terminator prefix per tile, blank rows that straddle tiles, their csv
+//                      row indices -> ms_scan_summary
+//   ms_parse_kernel    pass 2, one CTA per tile: row starts from the masks, then one LANE per row with the lanes
+//                      of a warp in lockstep over the columns of a chunk - each lane walks its row and finds a
+//                      field's end while parsing it: correctly rounded decimal -> double, coalesced stores
+//                      into channel-major float64 arrays (no field-offset table, no transpose staging)
+//   ms_row_index_kernel / ms_parse_rows_kernel   the same result for buffers with rows longer than a tile's overhang
 //
-// Replaces the per-row Python of the reference (reader.py:886-948, aggregator.py:96-124,
-// 229-241, user_data.py:391-396); see include/ms_b200.h for the boundary.
+// This path answers for EVERY input (quoted fields, any number of blank rows, errors in the reference's words);
+// ms_load_fused hands over to it whatever it declines.  Replaces the per-row Python of the reference
+// (reader.py:886-948, aggregator.py:96-124, 229-241, user_data.py:391-396); see include/ms_b200.h for the boundary.
 #include <stdio.h>
 
 #include "ms_common.cuh"

@@ -1,26 +1,64 @@
 // Trial windowing kernels (project/segment.py of the reference).
 //
-//   ms_phase_valid_kernel   per sample: does a run of >= min_phase_size samples with exactly
-//                           one / exactly two loaded force plates start here?  -> two bitmaps
-//   ms_transition_chase_kernel  one CTA: the alternating 1-leg / 2-leg search of
-//                           _transition_indices (segment.py:667-755) over the bitmaps
+//   ms_segment_kernel       per sample: does a run of >= min_phase_size samples with exactly one / exactly two
+//                           loaded force plates start here?  -> two bitmaps; then, in the block that finishes
+//                           last, the alternating 1-leg / 2-leg search of _transition_indices
+//                           (segment.py:667-755) over the bitmaps and the phase-window row ranges
 //   ms_cut_windows_kernel   DeviceData.__getitem__(slice) (user_data.py:727-731) for a batch
 //                           of windows over a channel-major array
 #include <stdio.h>
 
+#include <string.h>
+
 #include "ms_common.cuh"
 
-extern "C" int64_t ms_transitions_workspace_bytes(int64_t n) { return 2 * ((n + 31) / 32 + 1) * 4; }
+extern "C" int64_t ms_transitions_workspace_bytes(int64_t n) { return 2 * ((n + 31) / 32 + 1) * 4 + 16; }  // two bitmaps + a block counter
 
 // loaded(i) = value != 0; NaN != 0 is true, as in numpy (segment.py:716-721)
+// ---------------------------------------------------------------------------------------------------
+// The whole transition search in ONE launch: every block writes its words of the two "a phase may start here"
+// bitmaps; the block that finishes last (a counter in the workspace) then runs the 40 dependent searches with one
+// warp - 1024 samples per step, each step one L2 round trip, the bitmaps read past L1 because other blocks wrote
+// them - and turns the transitions into the row ranges of the phase (or cycle) windows of up to
+// MS_MAX_WINDOW_PLANS devices, so that the gathers can be queued right behind without the host in between.
+struct MsPlansArg {
+    ms_window_plan p[MS_MAX_WINDOW_PLANS];
+    int n;
+};
+
+__device__ void ms_plan_windows(const int64_t* __restrict__ transitions, int found, int num_segments, const ms_window_plan& pl) {
+    const int per_trecho = pl.cycles ? 2 : 8, span = pl.cycles ? 4 : 1, n_windows = 4 * per_trecho;
+    const bool ok = found >= num_segments && num_segments >= 40;
+    int64_t off = 0;
+    for (int w = 0; w < n_windows; w++) {
+        int64_t a = 0, b = 0;
+        if (ok) {
+            const int j = 10 * (w / per_trecho) + 1 + (w % per_trecho) * span;
+            a = transitions[j] / pl.divisor;
+            b = (transitions[j + span] - 1) / pl.divisor;
+            a = a < 0 ? 0 : (a > pl.n_rows ? pl.n_rows : a);
+            b = b < a ? a : (b > pl.n_rows ? pl.n_rows : b);
+        }
+        pl.d_starts[w] = a;
+        pl.d_stops[w] = b;
+        pl.d_offsets[w] = off;
+        off += (b - a) * pl.n_channels;
+    }
+    pl.d_offsets[n_windows] = off;
+}
+
 __global__ void __launch_bounds__(256)
-    ms_phase_valid_kernel(const double* __restrict__ left, const double* __restrict__ right, int64_t n, int min_phase,
-                          uint32_t* __restrict__ valid1, uint32_t* __restrict__ valid2) {
-    const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    ms_segment_kernel(const double* __restrict__ left, const double* __restrict__ right, int64_t n, int min_phase,
+                      uint32_t* __restrict__ valid1, uint32_t* __restrict__ valid2, unsigned int* __restrict__ counter,
+                      int num_segments, int64_t* __restrict__ transitions, int32_t* __restrict__ loaded,
+                      int32_t* __restrict__ n_found, const MsPlansArg plans) {
+    __shared__ bool s_last;
+    const int tid = threadIdx.x, lane = tid & 31;
+    // ---- part 1: this block's words of the bitmaps (segment.py:716-731)
+    const int64_t i = (int64_t)blockIdx.x * blockDim.x + tid;
     bool v1 = false, v2 = false;
     if (i < n) {
-        // correct_activation[ind : ind + min_phase_size].all() - the slice is cut at the end
-        // of the signal (segment.py:730)
+        // correct_activation[ind : ind + min_phase_size].all() - the slice is cut at the end of the signal
         const int64_t end = min(n, i + (int64_t)min_phase);
         v1 = v2 = true;
         for (int64_t j = i; j < end; j++) {
@@ -36,85 +74,86 @@ __global__ void __launch_bounds__(256)
         }
     }
     const uint32_t w1 = __ballot_sync(0xffffffffu, v1), w2 = __ballot_sync(0xffffffffu, v2);
-    if ((threadIdx.x & 31) == 0 && i < n + 32) {
-        const int64_t w = i >> 5;
-        if (w < (n + 31) / 32) {
-            valid1[w] = w1;
-            valid2[w] = w2;
+    const int64_t n_words = (n + 31) / 32;
+    if (lane == 0 && (i >> 5) < n_words) {
+        valid1[i >> 5] = w1;
+        valid2[i >> 5] = w2;
+    }
+    // ---- who is last?
+    __threadfence();
+    __syncthreads();
+    if (tid == 0) s_last = atomicInc(counter, gridDim.x - 1) == gridDim.x - 1;  // wraps to 0: ready for the next call
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    // ---- part 2 (one warp): the alternating search of _transition_indices (segment.py:738-755)
+    if (tid < 32) {
+        int64_t cursor = 0;
+        int found = 0;
+        for (int s = 0; s < num_segments; s++) {
+            const uint32_t* bm = (s & 1) ? valid2 : valid1;  // 1 leg, 2 legs, 1 leg, ...
+            int64_t base = cursor >> 5;
+            long long hit = -1;
+            while (base < n_words) {  // first set bit at index >= cursor, 32 words per step
+                const int64_t w = base + lane;
+                uint32_t word = w < n_words ? __ldcg(bm + w) : 0u;
+                if (w == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
+                const uint32_t any = __ballot_sync(0xffffffffu, word != 0u);
+                if (any) {
+                    const int src_lane = __ffs(any) - 1;
+                    const uint32_t first = __shfl_sync(0xffffffffu, word, src_lane);
+                    hit = (base + src_lane) * 32 + __ffs(first) - 1;
+                    break;
+                }
+                base += 32;
+            }
+            if (hit < 0) break;
+            cursor = hit;
+            if (lane == 0) {
+                transitions[s] = hit;
+                if (loaded) loaded[s] = (left[hit] != 0.0 ? 1 : 0) | (right[hit] != 0.0 ? 2 : 0);
+            }
+            found++;
         }
+        if (lane == 0) *n_found = found;
+        __syncwarp();
+        // ---- part 3: window plans, one lane each (the transitions were written by lane 0 of this warp)
+        if (lane < plans.n) ms_plan_windows(transitions, found, num_segments, plans.p[lane]);
     }
 }
 
-#define CHASE_THREADS 1024
-
-__global__ void __launch_bounds__(CHASE_THREADS)
-    ms_transition_chase_kernel(const double* __restrict__ left, const double* __restrict__ right, int64_t n,
-                               const uint32_t* __restrict__ valid1, const uint32_t* __restrict__ valid2,
-                               int num_segments, int64_t* __restrict__ transitions, int32_t* __restrict__ loaded,
-                               int32_t* __restrict__ n_found) {
-    __shared__ long long s_min;
-    const int tid = threadIdx.x;
-    const int64_t n_words = (n + 31) / 32;
-    int64_t cursor = 0;
-    int found = 0;
-    for (int s = 0; s < num_segments; s++) {
-        const uint32_t* bm = (s & 1) ? valid2 : valid1;  // 1 leg, 2 legs, 1 leg, ...
-        // first set bit at index >= cursor
-        int64_t base = cursor >> 5;
-        long long hit = -1;
-        while (base < n_words) {
-            if (tid == 0) s_min = 0x7fffffffffffffffll;
-            __syncthreads();
-            // two words per thread and round (independent loads): 65536 samples per round, so that a search
-            // across one gait phase usually ends in its first round - the rounds are what this kernel costs
-            const int64_t wa = base + tid, wb = wa + CHASE_THREADS;
-            uint32_t word_a = wa < n_words ? bm[wa] : 0u;
-            const uint32_t word_b = wb < n_words ? bm[wb] : 0u;
-            if (wa == (cursor >> 5)) word_a &= ~((1u << (cursor & 31)) - 1u);
-            if (word_a)
-                atomicMin(&s_min, (long long)(wa * 32 + __ffs(word_a) - 1));
-            else if (word_b)
-                atomicMin(&s_min, (long long)(wb * 32 + __ffs(word_b) - 1));
-            __syncthreads();
-            const long long m = s_min;
-            __syncthreads();
-            if (m != 0x7fffffffffffffffll) {
-                hit = m;
-                break;
-            }
-            base += 2 * CHASE_THREADS;
-        }
-        if (hit < 0) break;
-        cursor = hit;
-        if (tid == 0) {
-            transitions[s] = hit;
-            if (loaded) loaded[s] = (left[hit] != 0.0 ? 1 : 0) | (right[hit] != 0.0 ? 2 : 0);
-        }
-        found++;
+extern "C" int ms_segment_trial(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
+                                int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded,
+                                int32_t* d_n_found, const ms_window_plan* h_plans, int32_t n_plans, void* stream) {
+    if (!d_left_fz || !d_right_fz || !d_work || !d_transitions || !d_n_found || n < 0 || num_segments < 0)
+        return MS_E_INVALID;
+    if (n_plans < 0 || n_plans > MS_MAX_WINDOW_PLANS || (n_plans > 0 && !h_plans)) return MS_E_INVALID;
+    MsPlansArg plans;
+    memset(&plans, 0, sizeof plans);
+    for (int i = 0; i < n_plans; i++) {
+        const ms_window_plan& p = h_plans[i];
+        if (!p.d_starts || !p.d_stops || !p.d_offsets || p.divisor < 1 || p.n_rows < 0 || p.n_channels < 0) return MS_E_INVALID;
+        plans.p[plans.n++] = p;
     }
-    if (tid == 0) *n_found = found;
+    cudaStream_t st = (cudaStream_t)stream;
+    uint32_t* v1 = (uint32_t*)d_work;
+    uint32_t* v2 = v1 + ((n + 31) / 32 + 1);
+    unsigned int* counter = (unsigned int*)(v2 + ((n + 31) / 32 + 1));
+    MS_CUDA_CHECK(cudaMemsetAsync(counter, 0, sizeof(unsigned int), st));
+    const int64_t padded = (n + 31) / 32 * 32;
+    const unsigned blocks = (unsigned)(padded > 0 ? (padded + 255) / 256 : 1);
+    ms_segment_kernel<<<blocks, 256, 0, st>>>(d_left_fz, d_right_fz, n, min_phase_size, v1, v2, counter, num_segments,
+                                             d_transitions, d_loaded, d_n_found, plans);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
 }
 
 extern "C" int ms_find_transitions(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
                                    int32_t num_segments, void* d_work, int64_t* d_transitions, int32_t* d_loaded,
                                    int32_t* d_n_found, void* stream) {
-    if (!d_left_fz || !d_right_fz || !d_work || !d_transitions || !d_n_found || n < 0 || num_segments < 0)
-        return MS_E_INVALID;
-    cudaStream_t st = (cudaStream_t)stream;
-    uint32_t* v1 = (uint32_t*)d_work;
-    uint32_t* v2 = v1 + ((n + 31) / 32 + 1);
-    if (n > 0) {
-        const int64_t padded = (n + 31) / 32 * 32;
-        const unsigned blocks = (unsigned)((padded + 255) / 256);
-        ms_phase_valid_kernel<<<blocks, 256, 0, st>>>(d_left_fz, d_right_fz, n, min_phase_size, v1, v2);
-        MS_COUNT_LAUNCH();
-        MS_CUDA_CHECK(cudaGetLastError());
-    }
-    ms_transition_chase_kernel<<<1, CHASE_THREADS, 0, st>>>(d_left_fz, d_right_fz, n, v1, v2, num_segments,
-                                                           d_transitions, d_loaded, d_n_found);
-    MS_COUNT_LAUNCH();
-    MS_CUDA_CHECK(cudaGetLastError());
-    return MS_OK;
+    return ms_segment_trial(d_left_fz, d_right_fz, n, min_phase_size, num_segments, d_work, d_transitions, d_loaded,
+                            d_n_found, nullptr, 0, stream);
 }
 
 // ---------------------------------------------------------------------------------------------------

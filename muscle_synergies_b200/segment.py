@@ -92,7 +92,9 @@ class _TransitionSearch:
     behind the search can return its own small outputs in the same device->host copy."""
 
     @nat.on_tensor_device
-    def __init__(self, left_fz, right_fz, min_phase_size: int, num_segments: int, extra_words: int = 0):
+    def __init__(self, left_fz, right_fz, min_phase_size: int, num_segments: int, extra_words: int = 0, plans=()):
+        """plans: (divisor, n_rows, n_channels) per device whose 32 phase windows the same launch plans; plan i's
+        starts / stops / offsets land in extra[i * _PLAN_WORDS : (i + 1) * _PLAN_WORDS]."""
         import torch
 
         lib = nat.lib()
@@ -115,13 +117,18 @@ class _TransitionSearch:
         loaded, self.d_found = tail[:want], tail[want : want + 1]
         self.extra = self.res[want + self.tail_words :]
         self.stream = torch.cuda.current_stream(dev)
+        plans = list(plans)
+        c_plans = (nat.WindowPlan * max(1, len(plans)))()
+        for i, (divisor, n_rows, n_ch) in enumerate(plans):
+            base = self.extra.data_ptr() + 8 * i * _PLAN_WORDS
+            c_plans[i] = nat.WindowPlan(int(divisor), int(n_rows), int(n_ch), 0, base, base + 8 * 32, base + 8 * 64)
         nat.check(
-            lib.ms_find_transitions(
+            lib.ms_segment_trial(
                 left_fz.data_ptr(), right_fz.data_ptr(), n, int(min_phase_size), int(want), work.data_ptr(),
-                self.d_transitions.data_ptr(), loaded.data_ptr(), self.d_found.data_ptr(),
+                self.d_transitions.data_ptr(), loaded.data_ptr(), self.d_found.data_ptr(), c_plans, len(plans),
                 ctypes.c_void_p(self.stream.cuda_stream),
             ),
-            "ms_find_transitions",
+            "ms_segment_trial",
         )
         self._keep = (left_fz, right_fz, work)
 
@@ -240,9 +247,11 @@ class Segmenter:
         precut = list(cut_phases_of)
         if precut and num_segments < 40:
             raise ValueError("cut_phases_of needs the full 40 transitions")
+        in_launch = precut[: nat.MS_MAX_WINDOW_PLANS]  # their window plans come out of the search launch itself
         search = _TransitionSearch(_fz_tensor(left_fp), _fz_tensor(right_fp), min_phase_size, num_segments,
-                                   extra_words=_PLAN_WORDS * len(precut))
-        queued = [self._queue_phase_cuts(search, dev, i, left_fp) for i, dev in enumerate(precut)]
+                                   extra_words=_PLAN_WORDS * len(precut),
+                                   plans=[self._plan_args(dev, left_fp) for dev in in_launch])
+        queued = [self._queue_phase_cuts(search, dev, i, left_fp, planned=i < len(in_launch)) for i, dev in enumerate(precut)]
         try:
             self.transitions, self._loaded, extra = search.finish()
         finally:
@@ -255,13 +264,20 @@ class Segmenter:
         for i, (dev, out) in enumerate(queued):
             self._phase_cuts[id(dev)] = (dev, self._finish_phase_cuts(dev, out, extra[i * _PLAN_WORDS : (i + 1) * _PLAN_WORDS]))
 
-    def _queue_phase_cuts(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData):
+    @staticmethod
+    def _plan_args(dev: DeviceData, plate: DeviceData):
+        """(divisor, n_rows, n_channels) of ms_window_plan: force-plate sample index -> row of `dev`."""
+        src = dev.tensor
+        same_section = dev._frame_tracker.per_frame == plate._frame_tracker.per_frame
+        return (1 if same_section else plate._frame_tracker.num_subframes), int(src.shape[1]), int(src.shape[0])
+
+    def _queue_phase_cuts(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData, planned: bool = False):
         import torch
 
         with torch.cuda.device(dev.tensor.device):
-            return self._queue_phase_cuts_on_device(search, dev, slot, plate)
+            return self._queue_phase_cuts_on_device(search, dev, slot, plate, planned)
 
-    def _queue_phase_cuts_on_device(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData):
+    def _queue_phase_cuts_on_device(self, search: "_TransitionSearch", dev: DeviceData, slot: int, plate: DeviceData, planned: bool):
         """Plans (on the device) and gathers the 32 phase windows of `dev` behind the search."""
         import torch
 
@@ -274,9 +290,10 @@ class Segmenter:
         starts, stops, offsets = meta[:32], meta[32:64], meta[64:97]
         out = torch.empty(max(1, n_ch * n_rows), dtype=torch.float64, device=src.device)  # upper bound: every row once
         sptr = ctypes.c_void_p(search.stream.cuda_stream)
-        nat.check(lib.ms_plan_phase_windows(search.d_transitions.data_ptr(), search.d_found.data_ptr(), search.want, 0,
-                                            divisor, n_rows, n_ch, starts.data_ptr(), stops.data_ptr(),
-                                            offsets.data_ptr(), sptr), "ms_plan_phase_windows")
+        if not planned:
+            nat.check(lib.ms_plan_phase_windows(search.d_transitions.data_ptr(), search.d_found.data_ptr(), search.want, 0,
+                                                divisor, n_rows, n_ch, starts.data_ptr(), stops.data_ptr(),
+                                                offsets.data_ptr(), sptr), "ms_plan_phase_windows")
         if n_ch:
             nat.check(lib.ms_cut_windows(src.data_ptr(), int(src.stride(0)), n_ch, starts.data_ptr(), stops.data_ptr(),
                                          offsets.data_ptr(), 32, out.data_ptr(), n_rows, sptr), "ms_cut_windows")

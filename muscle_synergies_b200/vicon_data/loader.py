@@ -356,6 +356,8 @@ class ViconLoader:
             cap2 = int(h["rows"][1] * scale * 1.05) + 64
             arena = h["keep"][0] * cap1 + 2 + h["keep"][1] * cap2
             row_len = h["row_len"]
+            # a tile stages this much past its end: room for a row twice the longest average of the last file
+            overhang = h.get("overhang") or min(nat.MS_MAX_ROW_BYTES, max(1024, -(-int(2 * max(row_len, h["row_len2"]) + 64) // 512) * 512))
         else:
             m1 = HeaderMachine(SectionType.FORCES_EMG)
             try:
@@ -372,14 +374,15 @@ class ViconLoader:
             cap1 = int(n / row_len * 1.03) + 64
             cap2 = 0  # the second section takes what is left
             arena = (m1.layout.num_cols - 2) * cap1 + 2 + n // 12 + 4096
-        tile = nat.MS_TILE_BYTES
-        groups = int((tile + row_len / 2) // (32 * row_len))
+            overhang = nat.MS_MAX_ROW_BYTES
+        tile = 0  # the largest tile that fits beside the overhang
+        groups = int((nat.MS_TILE_BYTES + row_len / 2) // (32 * row_len))
         if groups >= 1 and TUNE_TILE:
             # just under a multiple of 32 rows per tile: the kernel parses rows in groups of 32 lanes
-            tile = max(4096, min(tile, int((32 * groups - 2) * row_len) // 16 * 16))
+            tile = max(4096, min(nat.MS_TILE_BYTES, int((32 * groups - 2) * row_len) // 16 * 16))
         if FORCE_TILE is not None:
-            tile = int(FORCE_TILE)
-        return arena, cap1, cap2, tile
+            tile, overhang = int(FORCE_TILE), nat.MS_MAX_ROW_BYTES
+        return arena, cap1, cap2, tile, overhang
 
     def _fmeta_acquire(self):
         if self._fmeta_pool:
@@ -396,7 +399,7 @@ class ViconLoader:
         sizes = self._fused_sizes(src, name)
         if sizes is None:
             return self._decline("no size estimate", back_off=False)
-        arena_elems, cap1, cap2, tile = sizes
+        arena_elems, cap1, cap2, tile, overhang = sizes
         stream, sptr = self._stream_ptr()
         meta = self._fmeta_acquire()
         d_meta, h_meta = meta
@@ -404,12 +407,25 @@ class ViconLoader:
             arena = torch.empty(arena_elems, dtype=torch.float64, device=self.device)
             ws_bytes = int(self.lib.ms_load_workspace_bytes(src.n, tile))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
-            plan = nat.LoadPlan(arena.data_ptr(), arena_elems, (ctypes.c_int64 * 2)(cap1, cap2), tile, 0)
+            plan = nat.LoadPlan(arena.data_ptr(), arena_elems, (ctypes.c_int64 * 2)(cap1, cap2), tile, overhang)
             nat.check(self.lib.ms_load_fused(src.d_bytes.data_ptr(), src.n, ctypes.byref(plan), ws.data_ptr(), ws_bytes,
                                              d_meta.data_ptr(), d_meta.data_ptr() + _FMETA_PEEK, sptr), "ms_load_fused")
             h_meta.copy_(d_meta, non_blocking=True)
             copied = torch.cuda.Event()
             copied.record(stream)
+        # While the kernel runs: the objects of a file that looks like the previous one (same header text -> the same
+        # cached layouts).  Whether it does is checked below, once the header text is back; row counts and the
+        # arena views are filled in then.
+        ahead = None
+        prev_layouts = (self._history or {}).get("layouts")
+        if prev_layouts is not None:
+            try:
+                guess = _Plan()
+                guess.layouts = prev_layouts
+                guess_blocks = [SectionBlock(None, 0), SectionBlock(None, 0)]
+                ahead = (_build(guess, guess_blocks), guess_blocks)
+            except (TypeError, ValueError, KeyError):
+                ahead = None  # Builder.build would raise: on the ordinary path below, after the rows are known good
         copied.synchronize()
         host = h_meta.numpy()
         res = nat.LoadResult.from_buffer_copy(host[: ctypes.sizeof(nat.LoadResult)].tobytes())
@@ -420,6 +436,9 @@ class ViconLoader:
 
         if res.flags:
             # a wrong size guess (alone) is no reason to avoid the kernel: the two-pass run below seeds the next guess
+            if res.flags == 1 and overhang < nat.MS_MAX_ROW_BYTES and self._history is not None:
+                self._history["overhang"] = nat.MS_MAX_ROW_BYTES  # a row longer than the last file suggested
+                return self._decline("flags ROW_TOO_LONG (short overhang)", back_off=False)
             return self._decline("flags " + "|".join(v for k, v in nat.MS_LOAD_FLAG_NAMES.items() if res.flags & k),
                                  back_off=res.flags != 16)
         if res.status != nat.MS_ERR_NONE:
@@ -465,15 +484,23 @@ class ViconLoader:
         plan_.layouts = layouts
         first2 = _HEADER_LINES + rows[0] + 1 + _HEADER_LINES
         plan_.data_rows = [(_HEADER_LINES, _HEADER_LINES + rows[0]), (first2, first2 + rows[1])]
-        blocks = []
+        reuse = ahead is not None and layouts[0] is prev_layouts[0] and layouts[1] is prev_layouts[1]
+        blocks = ahead[1] if reuse else [SectionBlock(None, 0), SectionBlock(None, 0)]
         for s in (0, 1):
             keep, stride, off = int(res.n_keep[s]), int(res.stride[s]), int(res.out_offset[s])
-            block = arena[off : off + keep * stride].view(keep, stride)[: layouts[s].n_keep]
-            blocks.append(SectionBlock(block, rows[s]))
+            blocks[s].tensor = arena[off : off + keep * stride].view(keep, stride)[: layouts[s].n_keep]
+            blocks[s].n_rows = rows[s]
         sec1_bytes = int(res.blank_end[0]) + 1
+        keep_overhang = (self._history or {}).get("overhang")
         self._history = {"n": src.n, "rows": rows, "keep": [int(res.n_keep[0]), int(res.n_keep[1])],
-                         "row_len": max(1.0, sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1))}
-        data = _build(plan_, blocks)  # raises what Builder.build raises (user_data.py:310-433): the rows are clean
+                         "row_len": max(1.0, sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1)),
+                         "row_len2": max(1.0, (src.n - sec1_bytes) / max(1, rows[1] + _HEADER_LINES + 1)),
+                         "overhang": keep_overhang, "layouts": layouts}
+        if reuse:
+            data = ahead[0]
+            data.emg._frame_tracker._sampling_freq.num_frames = rows[1]  # one SamplingFreq behind every tracker
+        else:
+            data = _build(plan_, blocks)  # raises what Builder.build raises (user_data.py:310-433): the rows are clean
         data.blocks = blocks
         return data
 
@@ -561,7 +588,9 @@ class ViconLoader:
         if lays[0] is None or lays[1] is None or not (lays[0].complete and lays[1].complete) or plan.sec1_bytes <= 0:
             return
         self._history = {"n": src.n, "rows": rows, "keep": [lays[0].num_cols - 2, lays[1].num_cols - 2],
-                         "row_len": max(1.0, plan.sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1))}
+                         "row_len": max(1.0, plan.sec1_bytes / max(1, rows[0] + _HEADER_LINES + 1)),
+                         "row_len2": max(1.0, (src.n - plan.sec1_bytes) / max(1, rows[1] + _HEADER_LINES + 1)),
+                         "overhang": (self._history or {}).get("overhang")}
 
     def load_many(self, sources, names=None, to_host: bool = True, host_slots: int = 2, return_exceptions: bool = False):
         """Pipelined batch load: yields one ViconNexusData per source, in order.

@@ -54,7 +54,7 @@ def main():
         L.ms_load_fused.argtypes = [vp, i64, ctypes.POINTER(nat.LoadPlan), vp, i64, vp, vp, vp]
         ws_bytes = int(L.ms_load_workspace_bytes(n, tile))
         ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
-        plan = nat.LoadPlan(arena.data_ptr(), arena.numel(), (ctypes.c_int64 * 2)(rows_guess, 0), tile, 0)
+        plan = nat.LoadPlan(arena.data_ptr(), arena.numel(), (ctypes.c_int64 * 2)(rows_guess, 0), tile, int(os.environ.get("MS_AB_OVERHANG", "0")))
 
         def call():
             rc = L.ms_load_fused(d.data_ptr(), n, ctypes.byref(plan), ws.data_ptr(), ws_bytes, d_res.data_ptr(),
