@@ -86,40 +86,53 @@ __global__ void __launch_bounds__(256)
     __syncthreads();
     if (!s_last) return;
     __threadfence();
-    // ---- part 2 (one warp): the alternating search of _transition_indices (segment.py:738-755)
-    if (tid < 32) {
-        int64_t cursor = 0;
-        int found = 0;
-        for (int s = 0; s < num_segments; s++) {
-            const uint32_t* bm = (s & 1) ? valid2 : valid1;  // 1 leg, 2 legs, 1 leg, ...
-            int64_t base = cursor >> 5;
-            long long hit = -1;
-            while (base < n_words) {  // first set bit at index >= cursor, 32 words per step
-                const int64_t w = base + lane;
-                uint32_t word = w < n_words ? __ldcg(bm + w) : 0u;
-                if (w == (cursor >> 5)) word &= ~((1u << (cursor & 31)) - 1u);
-                const uint32_t any = __ballot_sync(0xffffffffu, word != 0u);
-                if (any) {
-                    const int src_lane = __ffs(any) - 1;
-                    const uint32_t first = __shfl_sync(0xffffffffu, word, src_lane);
-                    hit = (base + src_lane) * 32 + __ffs(first) - 1;
-                    break;
-                }
-                base += 32;
+    // ---- part 2: the alternating search of _transition_indices (segment.py:738-755) by this whole block, 65536
+    // samples per round (eight independent loads per thread, read past L1: other blocks wrote the bitmaps) - a search
+    // across one gait phase ends in its first round, the rest between two walks over the plates takes a few
+    __shared__ long long s_min;
+    const long long none = 0x7fffffffffffffffll;
+    int64_t cursor = 0;
+    int found = 0;
+    for (int s = 0; s < num_segments; s++) {
+        const uint32_t* bm = (s & 1) ? valid2 : valid1;  // 1 leg, 2 legs, 1 leg, ...
+        int64_t base = cursor >> 5;
+        long long hit = -1;
+        while (base < n_words) {
+            if (tid == 0) s_min = none;
+            __syncthreads();
+            uint32_t word[8];
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const int64_t w = base + tid + k * 256;
+                word[k] = w < n_words ? __ldcg(bm + w) : 0u;
+                if (w == (cursor >> 5)) word[k] &= ~((1u << (cursor & 31)) - 1u);
             }
-            if (hit < 0) break;
-            cursor = hit;
-            if (lane == 0) {
-                transitions[s] = hit;
-                if (loaded) loaded[s] = (left[hit] != 0.0 ? 1 : 0) | (right[hit] != 0.0 ? 2 : 0);
+            long long best = none;
+#pragma unroll
+            for (int k = 7; k >= 0; k--)
+                if (word[k]) best = (long long)((base + tid + k * 256) * 32 + __ffs(word[k]) - 1);  // the nearest wins
+            if (best != none) atomicMin(&s_min, best);
+            __syncthreads();
+            const long long m = s_min;
+            __syncthreads();
+            if (m != none) {
+                hit = m;
+                break;
             }
-            found++;
+            base += 8 * 256;
         }
-        if (lane == 0) *n_found = found;
-        __syncwarp();
-        // ---- part 3: window plans, one lane each (the transitions were written by lane 0 of this warp)
-        if (lane < plans.n) ms_plan_windows(transitions, found, num_segments, plans.p[lane]);
+        if (hit < 0) break;
+        cursor = hit;
+        if (tid == 0) {
+            transitions[s] = hit;
+            if (loaded) loaded[s] = (left[hit] != 0.0 ? 1 : 0) | (right[hit] != 0.0 ? 2 : 0);
+        }
+        found++;
     }
+    if (tid == 0) *n_found = found;
+    __syncthreads();  // the transitions (thread 0's stores) before the plans read them
+    // ---- part 3: window plans, one thread each
+    if (tid < plans.n) ms_plan_windows(transitions, found, num_segments, plans.p[tid]);
 }
 
 extern "C" int ms_segment_trial(const double* d_left_fz, const double* d_right_fz, int64_t n, int32_t min_phase_size,
