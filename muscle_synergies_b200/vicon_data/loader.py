@@ -23,6 +23,7 @@ import ctypes
 import os
 import re
 import threading
+import time
 from typing import Callable, List, Optional, Tuple
 
 import numpy as np
@@ -60,6 +61,7 @@ _read_pool = None
 # FORCE_TILE: CSV bytes per thread block of the single-pass kernel (tests sweep it to move tile boundaries).
 FORCE_PATH = os.environ.get("MS_B200_LOADER") or None
 FORCE_TILE = None
+TIMELINE = None  # tools/step_timeline.py: a list that receives (label, perf_counter) marks of the single-pass path
 TUNE_TILE = os.environ.get("MS_B200_TUNE_TILE") == "1"  # size tiles to just under a multiple of 32 rows
 _FMETA_PEEK = 256  # offset of the two header peeks behind ms_load_result in the single-pass meta buffer
 _FMETA_BYTES = _FMETA_PEEK + 2 * nat.MS_LOAD_PEEK
@@ -396,6 +398,8 @@ class ViconLoader:
         reading of the header text it sends back) says the file is not plain enough; the caller then runs the
         two-pass path, which handles - and words the errors of - everything."""
         torch = self.torch
+        mark = (lambda label: TIMELINE.append((label, time.perf_counter()))) if TIMELINE is not None else (lambda label: None)
+        mark("enter")
         sizes = self._fused_sizes(src, name)
         if sizes is None:
             return self._decline("no size estimate", back_off=False)
@@ -416,6 +420,7 @@ class ViconLoader:
         # While the kernel runs: the objects of a file that looks like the previous one (same header text -> the same
         # cached layouts).  Whether it does is checked below, once the header text is back; row counts and the
         # arena views are filled in then.
+        mark("launched")
         ahead = None
         prev_layouts = (self._history or {}).get("layouts")
         if prev_layouts is not None:
@@ -426,7 +431,9 @@ class ViconLoader:
                 ahead = (_build(guess, guess_blocks), guess_blocks)
             except (TypeError, ValueError, KeyError):
                 ahead = None  # Builder.build would raise: on the ordinary path below, after the rows are known good
+        mark("built ahead")
         copied.synchronize()
+        mark("kernel done")
         host = h_meta.numpy()
         res = nat.LoadResult.from_buffer_copy(host[: ctypes.sizeof(nat.LoadResult)].tobytes())
         peeks = [host[_FMETA_PEEK + s * nat.MS_LOAD_PEEK : _FMETA_PEEK + s * nat.MS_LOAD_PEEK + max(0, int(res.peek_bytes[s]))].tobytes()
@@ -502,6 +509,7 @@ class ViconLoader:
         else:
             data = _build(plan_, blocks)  # raises what Builder.build raises (user_data.py:310-433): the rows are clean
         data.blocks = blocks
+        mark("returned")
         return data
 
     # ---- two passes ------------------------------------------------------------------------------------
