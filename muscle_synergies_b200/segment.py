@@ -16,6 +16,7 @@ alternations the reference silently re-appends a stale index (:745-752); this im
 raises ValueError instead.  Parity is claimed only when all transitions exist.
 """
 import ctypes
+import os
 import threading
 from collections import OrderedDict
 from enum import Enum, auto
@@ -233,6 +234,9 @@ class _WindowViews(Sequence):
 
 
 _PLAN_WORDS = 32 + 32 + 33  # starts, stops, offsets of the 32 phase windows of one device
+# Cross-check every device-planned window against the host's index arithmetic (the tests switch it on; it costs
+# 64 conversions per device and trial on the critical path of a step, for an identity the tests establish)
+VERIFY_DEVICE_PLAN = os.environ.get("MS_B200_VERIFY_PLAN") == "1"
 
 
 class Segmenter:
@@ -258,11 +262,32 @@ class Segmenter:
             check = getattr(data, "check", None)
             if check is not None:
                 check()  # a parse error of a deferred load comes first, as it would have at load time
-        self._segments = organize_transitions(left_fp.to_framesubfr, self.transitions, self._loaded,
-                                              getattr(left_fp, "to_framesubfr_many", None))
+        # The (frame, subframe) slices of all 32 phases are made when first asked for (get_times_of ...): 64
+        # conversions that the device-side window plan does not need.  What building them could raise is raised
+        # here, where the reference raises it (segment.py:852-879, user_data.py:575-597).
+        self._plate = left_fp
+        self._segments_made = None
+        if len(self.transitions) >= 40:
+            for n in range(len(Trecho)):
+                if self._loaded[10 * n + 2] in (0, 3):
+                    raise ValueError(
+                        "expected index corresponding to a phase in which there is ground reaction for exactly one leg."
+                    )
+            bounds = [self.transitions[j] for n in range(len(Trecho)) for j in (10 * n + 1, 10 * n + 9)]
+            if min(bounds) - 0 < 0 or max(bounds) > left_fp._frame_tracker.final_index:
+                self._segments  # out of the device's rows: the conversion raises the reference's IndexError
+        else:
+            self._segments
         self._phase_cuts = {}
         for i, (dev, out) in enumerate(queued):
             self._phase_cuts[id(dev)] = (dev, self._finish_phase_cuts(dev, out, extra[i * _PLAN_WORDS : (i + 1) * _PLAN_WORDS]))
+
+    @property
+    def _segments(self):
+        if self._segments_made is None:
+            self._segments_made = organize_transitions(self._plate.to_framesubfr, self.transitions, self._loaded,
+                                                       getattr(self._plate, "to_framesubfr_many", None))
+        return self._segments_made
 
     @staticmethod
     def _plan_args(dev: DeviceData, plate: DeviceData):
@@ -302,14 +327,15 @@ class Segmenter:
     def _finish_phase_cuts(self, dev: DeviceData, out, meta):
         meta = meta.tolist()
         starts, stops, offsets = meta[:32], meta[32:64], meta[64:97]
-        # the device planned the row ranges; the host path must agree (and raises what it would raise)
-        windows = [w[3] for w in self.all_phase_windows()]
-        flat = dev.to_index_many([b for w in windows for b in (w.start, w.stop)])
-        n_rows = int(dev.tensor.shape[1])
-        for i in range(32):
-            a = min(flat[2 * i], n_rows)
-            if (starts[i], stops[i]) != (a, max(a, min(flat[2 * i + 1], n_rows))):
-                raise AssertionError("device-planned phase window differs from the host's")
+        if VERIFY_DEVICE_PLAN:
+            # the device planned the row ranges; the host path (get_times_of -> DeviceData.to_index) must agree
+            windows = [w[3] for w in self.all_phase_windows()]
+            flat = dev.to_index_many([b for w in windows for b in (w.start, w.stop)])
+            n_rows = int(dev.tensor.shape[1])
+            for i in range(32):
+                a = min(flat[2 * i], n_rows)
+                if (starts[i], stops[i]) != (a, max(a, min(flat[2 * i + 1], n_rows))):
+                    raise AssertionError("device-planned phase window differs from the host's")
         return _WindowViews(out, int(dev.tensor.shape[0]), starts, stops, offsets)
 
     def phase_cuts(self, device: DeviceData):

@@ -10,6 +10,8 @@ if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
 GOLDEN = os.path.join(ROOT, "tests", "golden")
+# under test every device-planned phase window is cross-checked against the host's index arithmetic (segment.py)
+os.environ.setdefault("MS_B200_VERIFY_PLAN", "1")
 
 
 def pytest_configure(config):
