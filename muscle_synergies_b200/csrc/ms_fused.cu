@@ -198,15 +198,23 @@ __device__ __forceinline__ double2 lds_d2(uint32_t a) {
     return v;
 }
 
-// Parses the field that starts at *pp, advances *pp past its delimiter; true when that delimiter ended the row.
+// The field that starts at byte p of the staged region: its end (the delimiter's position) from the delimiter masks,
+// and - when it has one of the common shapes - its value.  Returns false for every other field: the caller queues it
+// for the general parser (ms_slow_fields), so that this path has no branches the lanes of a warp could part on.
 // sreg / sdm / slut: shared-window addresses of reg[0], the delimiter masks and the MsFieldLut.
-__device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, uint32_t sreg, uint32_t sdm, uint32_t slut,
-                                              int* pp, uint64_t* bits_out, unsigned long long* status, long long t0) {
-    const int p = *pp;
-    const uint32_t sd = sdm + ((p >> 4) << 1);
-    const uint32_t dm = ((lds_u16(sd + 2) << 16) | lds_u16(sd)) >> (p & 15);
-    const int L = __ffs(dm) - 1;  // bytes before the field's delimiter; -1: none within reach
+__device__ __forceinline__ bool ms_field_fast(uint32_t sreg, uint32_t sdm, uint32_t slut, int p, int* e_out, uint64_t* bits_out) {
+    uint32_t sd = sdm + ((p >> 4) << 1);
+    uint32_t dm = ((lds_u16(sd + 2) << 16) | lds_u16(sd)) >> (p & 15);
+    int L = __ffs(dm) - 1;  // bytes before the field's delimiter
+    if (dm == 0u) {
+        // none within reach (a field of 17 .. 32 bytes or more): walk the masks; the row's line end stops the walk
+        int seg = (p >> 4) + 2;
+        uint32_t m;
+        while ((m = lds_u16(sdm + (seg << 1))) == 0u) seg++;
+        L = (seg << 4) + __ffs(m) - 1 - p;
+    }
     const int e = p + L;
+    *e_out = e;
     // the 12 bytes that end at the delimiter
     const int a = e - 12;
     const uint32_t sw = sreg + (a & ~3);
@@ -219,16 +227,16 @@ __device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, u
     const uint32_t n0 = ((t0w + 0x76767676u) | t0w) & in.x & 0x80808080u, n1 = ((t1w + 0x76767676u) | t1w) & in.y & 0x80808080u,
                    n2 = ((t2w + 0x76767676u) | t2w) & in.z & 0x80808080u;
     const uint32_t M = ms_gather4(n0) | (ms_gather4(n1) << 4) | (ms_gather4(n2) << 8);
-    const unsigned c0 = lds_u8(sreg + p), ce = lds_u8(sreg + e);
+    const unsigned c0 = lds_u8(sreg + p);
     const uint32_t neg = c0 == '-' ? 1u : 0u;
-    const uint32_t Md = M & ~(neg << (12 - L));  // what is left must be the point
-    const int dotj = 31 - __clz(Md);              // -1: no point
+    const uint32_t Md = M & ~(neg << ((12 - L) & 31));  // what is left must be the point
+    const int dotj = 31 - __clz(Md);                      // -1: no point
     const uint32_t hasdot = Md != 0 ? 1u : 0u;
     const unsigned cd = lds_u8(sreg + a + (dotj & 15));
     const int nfrac = hasdot ? 11 - dotj : 0;
     const int ndig = L - (int)neg - (int)hasdot;
     // the point taken out: chars before it from the view shifted by one byte
-    const uint4 keep = lds_v4(slut + ((hasdot ? nfrac : 12) << 4));
+    const uint4 keep = lds_v4(slut + ((hasdot ? nfrac & 15 : 12) << 4));
     const uint4 dig = lds_v4(slut + ((ndig & 15) << 4));
     const uint32_t h0 = t0w << 8, h1 = __funnelshift_l(t0w, t1w, 8), h2 = __funnelshift_l(t1w, t2w, 8);
     const uint32_t g0 = ((t0w & keep.x) | (h0 & ~keep.x)) & dig.x, g1 = ((t1w & keep.y) | (h1 & ~keep.y)) & dig.y,
@@ -236,22 +244,35 @@ __device__ __forceinline__ bool ms_field_next(const uint8_t* __restrict__ reg, u
     const uint32_t v0 = ms_digits4_dp(g0);
     const uint32_t N = (v0 * 10000u + ms_digits4_dp(g1)) * 10000u + ms_digits4_dp(g2);
     // 1 to 12 digits whose value fits 32 bits (leading zeros are free: "-0.000944047" has ten digits)
-    bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && ndig >= 1 && v0 <= 41u && (!hasdot || cd == '.');
-    const double2 pw = lds_d2(slut + 256 + (nfrac << 4));
+    const bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && ndig >= 1 && v0 <= 41u && (!hasdot || cd == '.');
+    const double2 pw = lds_d2(slut + 256 + ((nfrac & 15) << 4));
     const double an = (double)N;
     const double q0 = __dmul_rn(an, pw.y);
     const double r = __fma_rn(-q0, pw.x, an);
-    uint64_t bits = ms_double_to_bits(__fma_rn(r, pw.y, q0)) | ((uint64_t)neg << 63);
-    if (L == 0) {  // an empty field: None -> NaN (reader.py:944-948, user_data.py:396)
-        bits = MS_NAN_BITS;
-        fast = true;
+    const uint64_t bits = ms_double_to_bits(__fma_rn(r, pw.y, q0)) | ((uint64_t)neg << 63);
+    // an empty field is None -> NaN (reader.py:944-948, user_data.py:396)
+    *bits_out = L == 0 ? MS_NAN_BITS : bits;
+    return fast || L == 0;
+}
+
+// The fields ms_field_fast left: exponents, blanks around numbers, '+', inf / nan, long mantissas, Unicode digits,
+// and everything float() rejects.  Queued by the lanes that met them ({p, e, arena index}), parsed here by the whole
+// block after the tile's items - densely, instead of by one or two lanes of a warp in the middle of its column.
+#define FUSED_SLOW_CAP (FUSED_MAX_NSEG * 2 / 8)  // the queue lives where the terminator masks were
+__device__ __forceinline__ void ms_slow_fields(const uint8_t* __restrict__ reg, const uint2* __restrict__ queue, int n, double* __restrict__ arena,
+                                               unsigned long long* status, long long t0, int tid) {
+    for (int i = tid; i < n; i += FUSED_THREADS) {
+        const uint2 q = queue[i];
+        const int p = (int)(q.x & 0xffffu), e = (int)(q.x >> 16);
+        uint64_t bits = MS_NAN_BITS;
+        const int st = ms_parse_field(reg + p, reg + e, &bits);
+        if (st != MS_PARSE_OK) {
+            bits = MS_NAN_BITS;
+            atomicMin(status, ((unsigned long long)(t0 + p) << 3) |
+                                  (st == MS_PARSE_NONASCII ? MS_ERR_KIND_NON_ASCII : MS_ERR_KIND_BAD_FLOAT));
+        }
+        if (q.y != 0xffffffffu) arena[q.y] = ms_bits_to_double(bits);
     }
-    if (fast) {
-        *bits_out = bits;
-        *pp = e + 1;
-        return ce != ',';
-    }
-    return ms_parse_next(reg, pp, bits_out, status, t0);
 }
 
 __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
@@ -274,6 +295,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     __shared__ __align__(8) unsigned long long s_stage_bar;
     MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + FUSED_OFF_LUT);
     __shared__ uint32_t s_inv_groups;
+    __shared__ int s_slow_n;
+    uint2* const slow_queue = reinterpret_cast<uint2*>(smem_raw + FUSED_OFF_TMASK);  // P4 only: the terminator masks are done with
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     unsigned long long* const lb = reinterpret_cast<unsigned long long*>(reinterpret_cast<uint8_t*>(ws) + FUSED_LB_OFFSET);
@@ -297,6 +320,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         s_stop = 0;
         s_agg_ready = 0;
         s_fatal = 0;
+        s_slow_n = 0;
     }
     __syncthreads();
     const long long tile = (long long)s_tile;
@@ -305,6 +329,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
 #endif
     const int tile_bytes = args.tile_bytes, region = args.region_bytes;
     const long long t0 = tile * (long long)tile_bytes;
+
     const int tile_len = (int)min((long long)tile_bytes, n - t0);
     const int nseg = region >> 4;
 
@@ -759,9 +784,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         __syncthreads();
         if (s_stop) return;
         const int ncols = __ldcg(&desc->num_cols);
-        const int n_keep = __ldcg(&desc->n_keep);
         const long long out_stride = __ldcg(&desc->stride);
-        double* const out_base = args.arena + __ldcg(&desc->out_offset);
+        const long long out_offset = __ldcg(&desc->out_offset);
         const int nrows = hi - Ld + 1;
         const long long out_row0 = idx_lo + (Ld - lo) - 5;  // output row of local row Ld
         if (out_row0 + nrows > out_stride) {
@@ -792,7 +816,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         asm volatile("mov.u32 %0, %0;" : "+r"(sreg));
 #endif
         const uint32_t sdm = sreg + (FUSED_OFF_CMASK - FUSED_PAD), slut = sreg + (FUSED_OFF_LUT - FUSED_PAD);
-        unsigned long long* const status = reinterpret_cast<unsigned long long*>(&res->status);
+        double* const arena = args.arena;
+        const uint32_t stride32 = (uint32_t)out_stride, out_idx0 = (uint32_t)(out_offset + out_row0);
         for (;;) {
             int item = 0;
             if (lane == 0) item = atomicAdd(&s_next_item, 1);
@@ -824,16 +849,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                         if (p > row_end - 1) done = true;  // the comma belongs to a later row
                     }
                 }
-                double* out = out_base + (long long)(c_lo - 2) * out_stride + (out_row0 + r);
-                for (int c = c_lo; c < c_hi; c++, out += out_stride) {
+                // element index into the arena, 32 bits (the entry point refuses larger arenas)
+                uint32_t oi = out_idx0 + (uint32_t)(c_lo - 2) * stride32 + (uint32_t)r;
+                for (int c = c_lo; c < c_hi; c++, oi += stride32) {
                     uint64_t bits = MS_NAN_BITS;
-                    if (!done) done = ms_field_next(reg, sreg, sdm, slut, &p, &bits, status, t0);
-                    const int ch = c - 2;
-                    if (ch >= 0 && ch < n_keep) *out = ms_bits_to_double(bits);
+                    if (!done) {
+                        int e;
+                        if (!ms_field_fast(sreg, sdm, slut, p, &e, &bits)) {
+                            // for the general parser, after the items (Frame / Sub Frame: parsed for their errors only)
+                            const int slot = atomicAdd(&s_slow_n, 1);
+                            if (slot < FUSED_SLOW_CAP) slow_queue[slot] = make_uint2((uint32_t)p | ((uint32_t)e << 16), c >= 2 ? oi : 0xffffffffu);
+                            bits = MS_NAN_BITS;
+                        }
+                        done = lds_u8(sreg + e) != ',';
+                        p = e + 1;
+                    }
+                    if (c >= 2) arena[oi] = ms_bits_to_double(bits);  // Frame, Sub Frame are never stored
                 }
             }
         }
-        __syncthreads();  // s_chunk_col / s_next_item are reused by the next run
+        __syncthreads();
+        {
+            const int n_slow = s_slow_n;
+            if (n_slow > FUSED_SLOW_CAP && tid == 0) atomicOr(&res->flags, MS_LOAD_DENSE_ROWS);  // cannot happen below 896 odd fields a tile
+            ms_slow_fields(reg, slow_queue, min(n_slow, FUSED_SLOW_CAP), arena, reinterpret_cast<unsigned long long*>(&res->status), t0, tid);
+        }
+        __syncthreads();  // s_chunk_col / s_next_item / the queue are reused by the next run
+        if (tid == 0) s_slow_n = 0;
     }
 }
 
