@@ -505,6 +505,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
                 ctrl = ((x.x - 0x23232323u) | x.x) | ((x.y - 0x23232323u) | x.y) | ((x.z - 0x23232323u) | x.z) |
                        ((x.w - 0x23232323u) | x.w);
+                // the commas of the segment, exactly; P1b adds the line-end bytes of the segments the test hit
+                cmask[v] = (uint16_t)ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu),
+                                               ms_eq_flags(x.z, 0x2c2c2c2cu), ms_eq_flags(x.w, 0x2c2c2c2cu));
             }
             const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
             if (lane == 0 && v < nseg_) hitmap[v >> 5] = hits;
@@ -542,7 +545,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
                 const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
                 tmask[v] = (uint16_t)term;
-                cmask[v] = (uint16_t)(lf | cr);  // a field also ends at a line end; the commas join below
+                cmask[v] |= (uint16_t)(lf | cr);  // a field also ends at a line end: commas + line-end bytes = delimiters
                 my_terms += __popc(term);
                 if (mine) {
                     const int p0 = v << 4;
@@ -645,14 +648,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
             const uint32_t f = s_flags | fatal | (nbw > 2 ? MS_LOAD_MANY_BLANKS : 0u);
             if (f) atomicOr(&res->flags, f);
-        }
-        // delimiter mask of every segment = its commas (exact) + the line-end bytes P1b left
-        for (int v = wtid; v < nseg_; v += NW) {
-            const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
-            uint32_t cm = ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu), ms_eq_flags(x.z, 0x2c2c2c2cu),
-                                    ms_eq_flags(x.w, 0x2c2c2c2cu));
-            if ((hitmap[v >> 5] >> (v & 31)) & 1u) cm |= cmask[v];
-            cmask[v] = (uint16_t)cm;
         }
     }
     __syncthreads();
