@@ -472,7 +472,7 @@ def run_ours(args):
     ws_bytes = int(lib.ms_load_workspace_bytes(n, 0))
     ws = torch.empty(ws_bytes, dtype=torch.uint8, device=dev)
     d_res = torch.empty(256 + 2 * _native.MS_LOAD_PEEK, dtype=torch.uint8, device=dev)
-    plan = _native.LoadPlan(arena.data_ptr(), arena.numel(), (ctypes.c_int64 * 2)(rows[0] + 64, rows[1] + 64), 0, 0)
+    plan = _native.LoadPlan(arena.data_ptr(), arena.numel(), (ctypes.c_int64 * 2)(rows[0] + 64, rows[1] + 64), *getattr(loader, "last_plan", (0, 0)))  # tile, overhang: as the step's loads
     t_fused = time_kernel(lambda: _native.check(lib.ms_load_fused(d_bytes.data_ptr(), n, ctypes.byref(plan), ws.data_ptr(), ws_bytes,
                                                                    d_res.data_ptr(), d_res.data_ptr() + 256, sptr), "ms_load_fused"))
     fres = _native.LoadResult.from_buffer_copy(d_res[: ctypes.sizeof(_native.LoadResult)].cpu().numpy().tobytes())

@@ -36,6 +36,9 @@
 #define FUSED_MAX_REGION (FUSED_MAX_TILE + MS_MAX_ROW_BYTES)
 #define FUSED_MAX_NSEG (FUSED_MAX_REGION / 16)
 #define FUSED_PAD 16
+#ifndef FUSED_LB_WINDOWS
+#define FUSED_LB_WINDOWS 1  // 32-tile windows of look-back words fetched per round trip (A/B: 2 and 4 were 1.5 % and 3.5 % slower)
+#endif
 #define FUSED_BYTES_SMEM (FUSED_MAX_REGION + 2 * FUSED_PAD)
 #define FUSED_ROWS_CAP 1024  // rows that may start in one tile
 #define FUSED_HIT_WORDS (FUSED_MAX_NSEG / 32 + 2)
@@ -296,6 +299,8 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + FUSED_OFF_LUT);
     __shared__ uint32_t s_inv_groups;
     __shared__ int s_slow_n;
+    __shared__ __align__(16) MsSecDesc s_desc;  // the descriptor of the section this tile starts in, fetched by warp 0
+    __shared__ int s_desc_sec;                  // which section s_desc describes; -1: none (not published at the time)
     uint2* const slow_queue = reinterpret_cast<uint2*>(smem_raw + FUSED_OFF_TMASK);  // P4 only: the terminator masks are done with
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
@@ -321,6 +326,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         s_agg_ready = 0;
         s_fatal = 0;
         s_slow_n = 0;
+        s_desc_sec = -1;
     }
     __syncthreads();
     const long long tile = (long long)s_tile;
@@ -416,34 +422,68 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         pre.nb = 0;
         pre.dist = 0;
         if (tile > 0) {
+            // FUSED_LB_WINDOWS x 32 predecessors per L2 round trip: the nearest tile with an inclusive word is usually a
+            // hundred or more tiles back (everything younger is still between its own P3 and its own look-back), and a
+            // walk of one 32-tile window per round trip took four or five of them AFTER the last aggregate appeared
             long long j = tile - 1;
             for (;;) {
-                const long long idx = j - lane;
-                unsigned long long w = LB_INCLUSIVE << 62;  // before the first tile: nothing (no blank rows, no rows)
-                if (idx >= 0) w = ld_relaxed_u64(&lb[idx]);
-                const uint32_t state = (uint32_t)(w >> 62);
-                const uint32_t invalid = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INVALID);
-                const uint32_t inclusive = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INCLUSIVE);
-                const int count = inclusive ? __ffs(inclusive) : 32;  // lanes 0 .. count-1 are what is needed
-                const uint32_t need = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
-                if (invalid & need) {
-                    __nanosleep(100);
-                    continue;
-                }
-                LbVal val = lb_unpack(w);
+                unsigned long long wq[FUSED_LB_WINDOWS];
 #pragma unroll
-                for (int d = 1; d < 32; d <<= 1) {
-                    LbVal o;
-                    o.nb = __shfl_down_sync(0xffffffffu, val.nb, d);
-                    o.dist = __shfl_down_sync(0xffffffffu, val.dist, d);
-                    if (lane + d < count) val = lb_combine(o, val);
+                for (int q = 0; q < FUSED_LB_WINDOWS; q++) {
+                    const long long idx = j - 32 * q - lane;
+                    wq[q] = LB_INCLUSIVE << 62;  // before the first tile: nothing (no blank rows, no rows)
+                    if (idx >= 0) wq[q] = ld_relaxed_u64(&lb[idx]);
                 }
-                // lane 0: the tiles j - count + 1 .. j; they come before what was gathered so far
-                pre = lb_combine(val, pre);
-                if (inclusive) break;
-                j -= 32;
+                bool finished = false;
+                int used = 0;
+#pragma unroll
+                for (int q = 0; q < FUSED_LB_WINDOWS; q++) {
+                    if (finished || used < q) continue;
+                    const unsigned long long w = wq[q];
+                    const uint32_t state = (uint32_t)(w >> 62);
+                    const uint32_t invalid = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INVALID);
+                    const uint32_t inclusive = __ballot_sync(0xffffffffu, state == (uint32_t)LB_INCLUSIVE);
+                    const int count = inclusive ? __ffs(inclusive) : 32;  // lanes 0 .. count-1 are what is needed
+                    const uint32_t need = count >= 32 ? 0xffffffffu : ((1u << count) - 1u);
+                    if (invalid & need) continue;  // this window (and the older ones) again, after a pause
+                    LbVal val = lb_unpack(w);
+#pragma unroll
+                    for (int d = 1; d < 32; d <<= 1) {
+                        LbVal o;
+                        o.nb = __shfl_down_sync(0xffffffffu, val.nb, d);
+                        o.dist = __shfl_down_sync(0xffffffffu, val.dist, d);
+                        if (lane + d < count) val = lb_combine(o, val);
+                    }
+                    // lane 0: the tiles j - 32 q - count + 1 .. j - 32 q; they come before what was gathered so far
+                    pre = lb_combine(val, pre);
+                    used = q + 1;
+                    if (inclusive) finished = true;
+                }
+                if (finished) break;
+                j -= 32 * used;
+                if (used < FUSED_LB_WINDOWS) __nanosleep(40);
             }
         }
+        // The section this tile starts in is known now: fetch its descriptor (column count, block address, chunk
+        // tables) if it is published - every tile but the few next to the header.  The loads are in flight while lane 0
+        // waits for the workers; P4 then starts without the chain of L2 round trips it would spend asking for them.
+        constexpr int DESC_WORDS = (int)(sizeof(MsSecDesc) / 4), DESC_PER_LANE = (DESC_WORDS + 31) / 32;
+        uint32_t dv[DESC_PER_LANE];
+        const int sec0 = (int)__shfl_sync(0xffffffffu, pre.nb, 0);
+        bool have_desc = false;
+#ifndef FUSED_NO_DESC_PREFETCH
+        if (sec0 < 2) {
+            const uint32_t* dsrc = reinterpret_cast<const uint32_t*>(&ws->desc[sec0]);
+            have_desc = ld_acquire_u32(&ws->desc[sec0].ready) != 0u;
+            if (have_desc) {
+#pragma unroll
+                for (int i = 0; i < DESC_PER_LANE; i++) {
+                    const int wi = lane + 32 * i;
+                    dv[i] = wi < DESC_WORDS ? __ldcg(dsrc + wi) : 0u;
+                }
+            }
+        }
+#endif
         if (lane == 0) {
             // this tile's own share comes from the workers (shared memory)
             while (*(volatile int*)&s_agg_ready == 0) __nanosleep(20);
@@ -464,6 +504,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                     atomicOr(&res->have, MS_LOAD_HAVE_ROWS0 << incl.nb);
                 }
             }
+        }
+        if (have_desc) {
+            uint32_t* ddst = reinterpret_cast<uint32_t*>(&s_desc);
+#pragma unroll
+            for (int i = 0; i < DESC_PER_LANE; i++) {
+                const int wi = lane + 32 * i;
+                if (wi < DESC_WORDS) ddst[wi] = dv[i];
+            }
+            if (lane == 0) s_desc_sec = sec0;
         }
         {
             // the staged bytes are read by this warp too from P4 on: observe the bulk copy's completion (long done)
@@ -572,7 +621,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             const int mine_w = lane < WW ? s_warp_terms[lane] : 0;
             int sc = mine_w;
 #pragma unroll
-            for (int d = 1; d < 16; d <<= 1) {
+            for (int d = 1; d < 32; d <<= 1) {
                 const int o = __shfl_up_sync(0xffffffffu, sc, d);
                 if (lane >= d) sc += o;
             }
@@ -765,22 +814,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         // data rows: lines 5.. of the section
         const int Ld = lo + (int)max(0ll, 5 - idx_lo);
         if (Ld > hi) continue;
-        if (tid == 0) {
-            int stop = 0;
-            while (!ld_acquire_u32(&desc->ready)) {
-                if (*(volatile uint32_t*)&res->flags) {  // the tile that owns the header gave up: so does the caller
-                    stop = 1;
-                    break;
+        const bool local_desc = s_desc_sec == sec;  // block-uniform; s_desc was written before the barrier above
+        if (!local_desc) {
+            if (tid == 0) {
+                int stop = 0;
+                while (!ld_acquire_u32(&desc->ready)) {
+                    if (*(volatile uint32_t*)&res->flags) {  // the tile that owns the header gave up: so does the caller
+                        stop = 1;
+                        break;
+                    }
+                    __nanosleep(100);
                 }
-                __nanosleep(100);
+                s_stop = stop;
             }
-            s_stop = stop;
+            __syncthreads();
+            if (s_stop) return;
         }
-        __syncthreads();
-        if (s_stop) return;
-        const int ncols = __ldcg(&desc->num_cols);
-        const long long out_stride = __ldcg(&desc->stride);
-        const long long out_offset = __ldcg(&desc->out_offset);
+        const int ncols = local_desc ? s_desc.num_cols : __ldcg(&desc->num_cols);
+        const long long out_stride = local_desc ? s_desc.stride : __ldcg(&desc->stride);
+        const long long out_offset = local_desc ? s_desc.out_offset : __ldcg(&desc->out_offset);
         const int nrows = hi - Ld + 1;
         const long long out_row0 = idx_lo + (Ld - lo) - 5;  // output row of local row Ld
         if (out_row0 + nrows > out_stride) {
@@ -788,13 +840,15 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             continue;
         }
         const int groups = (nrows + 31) >> 5;
-        const bool tabulated = groups <= PARSE_TAB_GROUPS && __ldcg(&desc->chunk_cnt[groups - 1]) != 0;
-        if (tabulated && tid <= PARSE_MAX_CHUNKS) s_chunk_col[tid] = __ldcg(&desc->chunk_tab[groups - 1][tid]);
+        const int tab_cnt = groups > PARSE_TAB_GROUPS ? 0 : (local_desc ? (int)s_desc.chunk_cnt[groups - 1] : (int)__ldcg(&desc->chunk_cnt[groups - 1]));
+        const bool tabulated = tab_cnt != 0;
+        if (tabulated && tid <= PARSE_MAX_CHUNKS)
+            s_chunk_col[tid] = local_desc ? s_desc.chunk_tab[groups - 1][tid] : __ldcg(&desc->chunk_tab[groups - 1][tid]);
         if (tid == 0) {
             s_next_item = 0;
             s_inv_groups = (65536u + groups - 1) / groups;  // item / groups by multiply-shift (items < 2^10)
             if (tabulated)
-                s_nchunks = __ldcg(&desc->chunk_cnt[groups - 1]);
+                s_nchunks = tab_cnt;
             else
                 s_nchunks = ms_chunk_table(groups, ncols, s_chunk_col, FUSED_WARPS);
         }
@@ -887,7 +941,7 @@ static int ms_fused_overhang(int32_t overhang_bytes) {
 }
 static int ms_fused_tile_bytes(int32_t tile_bytes, int overhang) {
     const int largest = FUSED_MAX_REGION - overhang;
-    if (tile_bytes <= 0) return largest < FUSED_MAX_TILE ? largest : FUSED_MAX_TILE;
+    if (tile_bytes <= 0) return largest;  // short rows (a small overhang) leave more of the staged region to the tile
     int t = tile_bytes / 16 * 16;
     if (t < 4096) t = 4096;
     if (t > largest) t = largest;

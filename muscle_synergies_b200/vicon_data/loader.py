@@ -404,6 +404,7 @@ class ViconLoader:
         if sizes is None:
             return self._decline("no size estimate", back_off=False)
         arena_elems, cap1, cap2, tile, overhang = sizes
+        self.last_plan = (tile, overhang)  # what the kernel was asked for (bench.py times the kernel with the same)
         stream, sptr = self._stream_ptr()
         meta = self._fmeta_acquire()
         d_meta, h_meta = meta
