@@ -597,7 +597,9 @@ def run_ours(args):
         from muscle_synergies_b200.pipeline import synergies_for_files_sharded
 
         kw = dict(min_components=1, max_components=8, n_restarts=20, random_state=0, max_iter=200, tol=0.0)
-        synergies_for_files_sharded(paths[: world], loader=loader, **kw)  # warm-up: one file per rank
+        # warm-up, three files per rank: the pipeline is one trial deep, so its pinned result buffers and the allocator's
+        # blocks reach their steady state with the second trial in flight
+        synergies_for_files_sharded(paths[: 3 * world], loader=loader, **kw)
         barrier()
         t = time.perf_counter()
         table = synergies_for_files_sharded(paths, loader=loader, **kw)  # includes the host-side gather of the tables

@@ -76,10 +76,65 @@ def _batch_draws(torch, n, m, ranks, seeds, dev):
     return hit
 
 
+_pinned_pool = {}  # nbytes -> pinned uint8 tensors not on loan (results of deferred runs travel through them)
+
+
+def _pinned_take(torch, nbytes: int):
+    free = _pinned_pool.get(nbytes)
+    return free.pop() if free else torch.empty(nbytes, dtype=torch.uint8, pin_memory=True)
+
+
+def _pinned_give(buf):
+    free = _pinned_pool.setdefault(int(buf.numel()), [])
+    if len(free) < 4:
+        free.append(buf)
+
+
+class PendingNMF:
+    """A batch whose kernel is queued and whose results are on their way to pinned host memory: `result()` waits
+    for the copies and builds the NMFBatchResult.  Lets a caller queue the next trial's GPU work before it
+    looks at this one's (pipeline.synergies_for_files)."""
+
+    def __init__(self, torch, stream, ranks, seeds, n, m, device_arrays, keep):
+        self._ranks, self._seeds, self._n, self._m = ranks, seeds, n, m
+        self._keep = keep  # inputs of the kernel: alive until the copies below have run
+        self._bufs = []
+        for t in device_arrays:
+            t = t.contiguous()
+            buf = _pinned_take(torch, int(t.numel()) * t.element_size())
+            buf.view(t.dtype).copy_(t.reshape(-1), non_blocking=True)
+            self._bufs.append((buf, t.dtype, tuple(t.shape)))
+            self._keep.append(t)
+        self._event = torch.cuda.Event()
+        self._event.record(stream)
+        self._result = None
+
+    def result(self) -> NMFBatchResult:
+        if self._result is None:
+            self._event.synchronize()
+            out = []
+            for buf, dtype, shape in self._bufs:
+                out.append(buf.view(dtype).numpy().reshape(shape).copy())  # own memory: the pinned buffer goes back
+                _pinned_give(buf)
+            self._bufs, self._keep = [], []
+            self._result = _assemble(self._ranks, self._seeds, self._n, self._m, *out)
+        return self._result
+
+
+def _assemble(ranks, seeds, n, m, Wall, Hall, n_iter, err, vafs) -> NMFBatchResult:
+    P = len(ranks)
+    w_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * n)])
+    h_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * m)])
+    Ws = [Wall[w_off[p] : w_off[p + 1]].reshape(n, int(ranks[p])) for p in range(P)]
+    Hs = [Hall[h_off[p] : h_off[p + 1]].reshape(int(ranks[p]), m) for p in range(P)]
+    return NMFBatchResult(ranks, seeds, Ws, Hs, n_iter, err, vafs)
+
+
 def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int = 200, tol: float = 1e-4,
                    check_every: int = 10, init=None, device=None, x_index: Optional[Sequence[int]] = None,
-                   regime: Optional[str] = None) -> NMFBatchResult:
-    """Runs len(ranks) MU factorisations in one kernel launch.
+                   regime: Optional[str] = None, defer: bool = False) -> Union[NMFBatchResult, PendingNMF]:
+    """Runs len(ranks) MU factorisations in one kernel launch.  defer=True returns a PendingNMF right after the
+    launch (`.result()` gives the NMFBatchResult).
 
     X: non-negative (n samples x m muscles), or a stack (B, n, m) of such matrices (e.g. one per
     gait cycle) with x_index[p] naming the matrix of problem p; a numpy array, or a CUDA tensor
@@ -157,13 +212,11 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
             ),
             "ms_nmf_mu_batched" if resident else "ms_nmf_mu_stream",
         )
+        if defer:
+            return PendingNMF(torch, stream, ranks, seeds, n, m, [dW, dH, d_iter, d_err, d_vaf], [dX, work])
         Wall, Hall = dW.cpu().numpy(), dH.cpu().numpy()
         n_iter, err, vafs = d_iter.cpu().numpy(), d_err.cpu().numpy(), d_vaf.cpu().numpy()
-    w_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * n)])
-    h_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * m)])
-    Ws = [Wall[w_off[p] : w_off[p + 1]].reshape(n, int(ranks[p])) for p in range(P)]
-    Hs = [Hall[h_off[p] : h_off[p + 1]].reshape(int(ranks[p]), m) for p in range(P)]
-    return NMFBatchResult(ranks, seeds, Ws, Hs, n_iter, err, vafs)
+    return _assemble(ranks, seeds, n, m, Wall, Hall, n_iter, err, vafs)
 
 
 # ---- reference API ------------------------------------------------------------------------------------

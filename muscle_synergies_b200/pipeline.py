@@ -17,7 +17,7 @@ envelopes.  This module is an extension: the reference has no batch entry point.
 """
 from collections.abc import Mapping
 from dataclasses import dataclass, field
-from typing import Dict, Iterable, List, Optional, Sequence, Tuple
+from typing import Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
 import pandas
@@ -99,14 +99,30 @@ def cycle_windows(segmenter: Segmenter) -> List[Tuple[Trecho, Cycle, slice]]:
     return [(t, c, segmenter.get_times_of(t, c)) for t in Trecho for c in Cycle]
 
 
+class PendingTrial:
+    """A trial whose GPU work (segmentation, envelopes, the NMF launch, the copies of its results) is queued:
+    `finish()` waits for it and builds the TrialSynergies on the host."""
+
+    def __init__(self, finish):
+        self._finish, self._done = finish, None
+
+    def finish(self) -> "TrialSynergies":
+        if self._done is None:
+            self._done = self._finish()
+            self._finish = None
+        return self._done
+
+
 def trial_synergies(data: ViconNexusData, min_components: int = 1, max_components: int = 8, n_restarts: int = 20,
                     random_state: int = 0, max_iter: int = 200, tol: float = 1e-4, window_size: float = 0.5,
                     reduce_to: int = 200, segmenter: Optional[Segmenter] = None, keep_batch: bool = False,
-                    seeds: Optional[Sequence[int]] = None) -> TrialSynergies:
+                    seeds: Optional[Sequence[int]] = None, defer: bool = False) -> Union[TrialSynergies, PendingTrial]:
     """Segments a loaded trial and factorises the EMG envelope of each of its 8 gait cycles for
     every rank in [min_components, max_components] from `n_restarts` random initialisations
     (seeds random_state .. random_state + n_restarts - 1, sklearn `init="random"` draws; `seeds` names
-    them explicitly instead - the share of one GPU when the restarts of a trial are split over several)."""
+    them explicitly instead - the share of one GPU when the restarts of a trial are split over several).
+    defer=True queues the GPU work and returns a PendingTrial: the caller can queue the next trial before it
+    asks this one to `finish()` (the host-side tables of one trial are then built while the GPU factorises the next)."""
     muscles = data.emg.columns
     if not 1 <= min_components <= max_components <= len(muscles):
         raise ValueError("invalid number of components")
@@ -123,8 +139,16 @@ def trial_synergies(data: ViconNexusData, min_components: int = 1, max_component
     ranks = np.tile(np.repeat(np.array(sweep, dtype=np.int32), n_restarts), n_cyc)
     seeds = np.tile(seed_list, n_cyc * n_k)
     x_index = np.repeat(np.arange(n_cyc, dtype=np.int32), n_k * n_restarts)
-    res = nmf_mu_batched(env, ranks, seeds, max_iter=max_iter, tol=tol, x_index=x_index)
+    pending = nmf_mu_batched(env, ranks, seeds, max_iter=max_iter, tol=tol, x_index=x_index, defer=True)
 
+    def finish() -> TrialSynergies:
+        return _trial_tables(pending.result(), data, wins, sweep, n_restarts, ranks, seeds, muscles, env, keep_batch)
+
+    return PendingTrial(finish) if defer else finish()
+
+
+def _trial_tables(res, data, wins, sweep, n_restarts, ranks, seeds, muscles, env, keep_batch) -> TrialSynergies:
+    n_cyc, n_k = len(wins), len(sweep)
     labels = ["All signals"] + muscles
     err = res.err.reshape(n_cyc, n_k, n_restarts)
     best = err.argmin(axis=2)
@@ -156,14 +180,32 @@ def synergies_for_files(paths: Sequence[str], loader: Optional[ViconLoader] = No
     current one is analysed (ViconLoader.load_files).  Yields (path, TrialSynergies) in order; a
     file that fails to load or to segment yields (path, exception) instead."""
     loader = loader if loader is not None else ViconLoader()
+    caught = (ValueError, IndexError, KeyError)  # e.g. fewer than 40 transitions in the trial
+
+    def finished(item):
+        path, pending = item
+        if isinstance(pending, Exception):
+            return path, pending
+        try:
+            return path, pending.finish()
+        except caught as exc:
+            return path, exc
+
+    # one trial deep: the GPU work of trial i is queued before the host looks at the results of trial i - 1
+    prev = None
     for path, data in loader.load_files(paths, to_host=False):
         if isinstance(data, Exception):
-            yield path, data
-            continue
-        try:
-            yield path, trial_synergies(data, **kwargs)
-        except (ValueError, IndexError, KeyError) as exc:  # e.g. fewer than 40 transitions in the trial
-            yield path, exc
+            cur = (path, data)
+        else:
+            try:
+                cur = (path, trial_synergies(data, defer=True, **kwargs))
+            except caught as exc:
+                cur = (path, exc)
+        if prev is not None:
+            yield finished(prev)
+        prev = cur
+    if prev is not None:
+        yield finished(prev)
 
 
 # ---- several GPUs: one process per GPU, no collective on the data path (SURVEY.md section 8e) ---------------------

@@ -54,6 +54,7 @@ _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 
 _READ_CHUNK = 32 << 20
+_READ_CHUNK_MIN = 2 << 20
 _read_pool = None
 
 # Which kernels load a file: None = the single-pass kernel (ms_load_fused) with the two-pass path
@@ -75,13 +76,20 @@ def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callabl
     if _read_pool is None:
         from concurrent.futures import ThreadPoolExecutor
 
-        _read_pool = ThreadPoolExecutor(max_workers=max(2, min(8, (os.cpu_count() or 2) - 1)), thread_name_prefix="ms-read")
+        try:
+            cpus = len(os.sched_getaffinity(0))  # this process's share of the box (one rank per GPU binds a subset)
+        except AttributeError:
+            cpus = os.cpu_count() or 2
+        _read_pool = ThreadPoolExecutor(max_workers=max(2, min(8, cpus - 1)), thread_name_prefix="ms-read")
+    # two chunks per worker: a 100 MB trial keeps the whole pool busy (in 32 MB chunks it kept four threads busy)
+    workers = _read_pool._max_workers
+    chunk = min(_READ_CHUNK, max(_READ_CHUNK_MIN, -(-size // (2 * workers * _READ_CHUNK_MIN)) * _READ_CHUNK_MIN))
     fd = os.open(name, os.O_RDONLY)
     try:
         mem = memoryview(view)
 
         def part(off):
-            want = min(_READ_CHUNK, size - off)
+            want = min(chunk, size - off)
             got = 0
             while got < want:
                 k = os.preadv(fd, [mem[off + got : off + want]], off + got)
@@ -90,7 +98,7 @@ def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callabl
                 got += k
             return off, want
 
-        for off, want in _read_pool.map(part, range(0, size, _READ_CHUNK)):
+        for off, want in _read_pool.map(part, range(0, size, chunk)):
             if on_chunk is not None:
                 on_chunk(off, want)
     finally:
