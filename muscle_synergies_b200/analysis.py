@@ -7,8 +7,9 @@ solver="mu", beta_loss="frobenius", init="random" case runs as ONE CUDA launch f
 rank sweep x restarts grid (csrc/ms_nmf.cu), in fp32, with sklearn's initialisation
 (`RandomState(seed)`: H drawn first, then W - sklearn/decomposition/_nmf.py:_initialize_nmf)
 generated on the host so that a run is comparable to `NMF(solver="mu", init="random",
-random_state=seed)` at the same iteration count.  Other solvers / inits raise
-NotImplementedError: this stage is an extension, not a replacement of scikit-learn.
+random_state=seed)` at the same iteration count.  Every other call (sklearn's default solver="cd",
+nndsvd inits, regularisation ...) is forwarded to scikit-learn, exactly as the reference does
+(analysis.py:848-864): this stage is an extension, not a replacement of scikit-learn.
 """
 import ctypes
 import functools
