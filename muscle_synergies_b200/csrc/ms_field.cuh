@@ -20,9 +20,12 @@ static_assert(PARSE_CHUNK % 16 == 0 && PARSE_CHUNK * PARSE_THREADS == PARSE_REGI
 #define PARSE_MAX_CHUNKS 32
 #define PARSE_SMEM (PARSE_BYTES_SMEM + PARSE_NSEG * 2 + 32 + (PARSE_ROWS_CAP + 1) * 4)
 
+// widest chunk = MS_EXP_UNUM / MS_EXP_UDEN of a warp's fair share of the tile.  A/B on the single-pass kernel (T10 / T127):
+// 1/2 +2 %, 5/8 +0.7 %, 3/4 reference, 1/1 -1.3 % / -2.5 %, 5/4 -1.2 %, 3/2 -0.6 %: every chunk but a row's first costs a
+// walk over the row's comma masks to its first column, which outweighs the better balance of finer chunks.
 #ifndef MS_EXP_UNUM
-#define MS_EXP_UNUM 3
-#define MS_EXP_UDEN 4
+#define MS_EXP_UNUM 1
+#define MS_EXP_UDEN 1
 #endif
 // Column chunks of DECREASING width, handed out widest first (chunk-major), so that the last items a warp
 // can draw are small and the warps finish the tile together (uniform chunks left ~30 % of the warps idle at
