@@ -33,8 +33,27 @@ __device__ __forceinline__ uint32_t ms_ge_flags(uint32_t w, uint32_t n_rep) {
 // gathers flag bits 7,15,23,31 into bits 0..3
 __device__ __forceinline__ uint32_t ms_gather4(uint32_t flags) { return (flags * 0x00204081u) >> 28; }
 
+// Four flag words (0x80 in each matching byte) -> ordered 16-bit mask.  Integer dot products do the gathering: the
+// flags of a word times {1, 2, 4, 8} (or {16, 32, 64, 128}) add up to 128 x its four mask bits - six instructions
+// where multiply-and-shift per word took a dozen.
 __device__ __forceinline__ uint32_t ms_mask16(uint32_t f0, uint32_t f1, uint32_t f2, uint32_t f3) {
+#ifdef MS_NO_DP4A_MASKS
     return ms_gather4(f0) | (ms_gather4(f1) << 4) | (ms_gather4(f2) << 8) | (ms_gather4(f3) << 12);
+#else
+    const uint32_t lo = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(f3, 0x80402010u, __dp4a(f2, 0x08040201u, 0u));
+    return (hi * 256u + lo) >> 7;
+#endif
+}
+// the same for three words: a 12-bit mask
+__device__ __forceinline__ uint32_t ms_mask12(uint32_t f0, uint32_t f1, uint32_t f2) {
+#ifdef MS_NO_DP4A_MASKS
+    return ms_gather4(f0) | (ms_gather4(f1) << 4) | (ms_gather4(f2) << 8);
+#else
+    const uint32_t lo = __dp4a(f1, 0x80402010u, __dp4a(f0, 0x08040201u, 0u));
+    const uint32_t hi = __dp4a(f2, 0x08040201u, 0u);
+    return (hi * 256u + lo) >> 7;
+#endif
 }
 
 // Ordered 16-bit masks (bit i = byte i of the vector) of the structural bytes.

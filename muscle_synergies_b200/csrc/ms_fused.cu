@@ -229,7 +229,7 @@ __device__ __forceinline__ bool ms_field_fast(uint32_t sreg, uint32_t sdm, uint3
     // chars of the field that are not digits -> bit j of M (j = 0: 12 bytes before the delimiter)
     const uint32_t n0 = ((t0w + 0x76767676u) | t0w) & in.x & 0x80808080u, n1 = ((t1w + 0x76767676u) | t1w) & in.y & 0x80808080u,
                    n2 = ((t2w + 0x76767676u) | t2w) & in.z & 0x80808080u;
-    const uint32_t M = ms_gather4(n0) | (ms_gather4(n1) << 4) | (ms_gather4(n2) << 8);
+    const uint32_t M = ms_mask12(n0, n1, n2);
     const unsigned c0 = lds_u8(sreg + p);
     const uint32_t neg = c0 == '-' ? 1u : 0u;
     const uint32_t Md = M & ~(neg << ((12 - L) & 31));  // what is left must be the point
@@ -900,12 +900,13 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 }
                 // element index into the arena, 32 bits (the entry point refuses larger arenas)
                 uint32_t oi = out_idx0 + (uint32_t)(c_lo - 2) * stride32 + (uint32_t)r;
-                for (int c = c_lo; c < c_hi; c++, oi += stride32) {
+                int c = c_lo;
+#ifdef FUSED_OLD_LOOP
+                for (; c < c_hi; c++, oi += stride32) {
                     uint64_t bits = MS_NAN_BITS;
                     if (!done) {
                         int e;
                         if (!ms_field_fast(sreg, sdm, slut, p, &e, &bits)) {
-                            // for the general parser, after the items (Frame / Sub Frame: parsed for their errors only)
                             const int slot = atomicAdd(&s_slow_n, 1);
                             if (slot < FUSED_SLOW_CAP) slow_queue[slot] = make_uint2((uint32_t)p | ((uint32_t)e << 16), c >= 2 ? oi : 0xffffffffu);
                             bits = MS_NAN_BITS;
@@ -915,6 +916,30 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                     }
                     if (c >= 2) arena[oi] = ms_bits_to_double(bits);  // Frame, Sub Frame are never stored
                 }
+#else
+                // the fields the row has ...
+                if (!done) {
+                    while (c < c_hi) {
+                        int e;
+                        uint64_t bits;
+                        if (!ms_field_fast(sreg, sdm, slut, p, &e, &bits)) {
+                            // for the general parser, after the items (Frame / Sub Frame: parsed for their errors only)
+                            const int slot = atomicAdd(&s_slow_n, 1);
+                            if (slot < FUSED_SLOW_CAP) slow_queue[slot] = make_uint2((uint32_t)p | ((uint32_t)e << 16), c >= 2 ? oi : 0xffffffffu);
+                            bits = MS_NAN_BITS;
+                        }
+                        const bool last = lds_u8(sreg + e) != ',';
+                        p = e + 1;
+                        if (c >= 2) arena[oi] = ms_bits_to_double(bits);  // Frame, Sub Frame are never stored
+                        c++;
+                        oi += stride32;
+                        if (last) break;
+                    }
+                }
+                // ... and None -> NaN for the ones a short row does not have (reader.py:944-948, user_data.py:396)
+                for (; c < c_hi; c++, oi += stride32)
+                    if (c >= 2) arena[oi] = ms_bits_to_double(MS_NAN_BITS);
+#endif
             }
         }
         __syncthreads();
