@@ -440,12 +440,27 @@ def run_ours(args):
     data, cuts = step_resident()
     n_kept = sum(int(d.tensor.numel()) for d in list(data.forcepl) + [data.emg] + list(data.traj))
     b_alg = n + 8 * n_kept
+    def steps_streamed(k):
+        # the same K steps as a stream of trials (what a 1000-trial job is): load_device_many keeps the loader kernel of
+        # the next two trials queued on its own stream while the host finishes trial i's objects and runs Segmenter + the
+        # window gather on it - every step still ends with the 40 transitions and the 32 windows of ITS trial on the host
+        out = None
+        work = loader.work_stream  # high priority: the small kernels of a step run beside the next trial's loader kernel
+        for data in loader.load_device_many(((d_bytes, n) for _ in range(k)), depth=args.depth, stream=work):
+            with torch.cuda.stream(work):
+                seg = Segmenter(data, cut_phases_of=(data.emg,))
+                out = seg.phase_cuts(data.emg)
+        torch.cuda.current_stream().wait_stream(work)  # the closing event is recorded after the last step's kernels
+        return out
+
     for _ in range(max(3, args.warmup)):
         step_resident()
+    steps_streamed(max(3, args.warmup))
     path_used = dict(loader.stats)
+    ms_serial = timed(step_resident, args.steps)  # one trial at a time, the host's work between the kernels exposed
     launches0 = _native.launch_count()
     with ClockSampler(local_rank) as clocks:
-        ms_total = timed(step_resident, args.steps)
+        ms_total = timed(lambda: steps_streamed(args.steps), 1)
     launches = _native.launch_count() - launches0
     value = world * n * args.steps / (ms_total * 1e-3) / 1e9
 
@@ -634,7 +649,8 @@ def run_ours(args):
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
-            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "higher_is_better": True,
+            "warmup": max(3, args.warmup), "ms_per_step": ms_total / args.steps, "ms_per_step_serial": ms_serial / args.steps,
+            "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
             "config": {
                 "workload": WORKLOAD if layout == "T10" else layout, "csv_bytes_per_gpu": n, "kept_doubles_per_gpu": n_kept,
@@ -642,6 +658,9 @@ def run_ours(args):
                 "parallelism": f"{world} ranks, trials sharded by file, no data-path collective",
                 "host_cpus_bound": len(numa_cpus) if numa_cpus else None,
                 "loader_path": path_used,
+                "step": f"load + Segmenter + 32 EMG windows per trial; K trials streamed through ViconLoader.load_device_many "
+                        f"(depth {args.depth}: the next trials' loader kernels queued while the host works on this one); "
+                        "ms_per_step_serial = the same step one trial at a time",
             },
             "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": n, "d2h_bytes_per_step": d2h,
                     "ms_per_step": ms_e2e / e2e_steps, "steps": e2e_steps,
@@ -673,6 +692,7 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--layout", default="T10", help="synthetic layout (tools/synth_vicon.py LAYOUTS)")
     ap.add_argument("--no-cpu", action="store_true", help="skip the CPU baseline leg")
+    ap.add_argument("--depth", type=int, default=2, help="trials in flight in the streamed headline loop (load_device_many)")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -26,6 +26,15 @@
 #ifndef FUSED_THREADS
 #define FUSED_THREADS 512
 #endif
+// Build-time variants kept for A/B runs (tools/ab_fused.py); the defaults are what measured best on T10 / T127:
+//   FUSED_LATE_COMMAS  comma masks found after the tile's aggregate is published (P1c) instead of in the first sweep
+//   FUSED_WALK64       the walk to a column chunk's first field reads four segments' delimiter masks per step
+//   FUSED_PIN_LUT      the field LUT's shared-window address kept in one register across the field loop
+#ifndef FUSED_AB_BASE
+#define FUSED_LATE_COMMAS
+#define FUSED_WALK64
+#define FUSED_PIN_LUT
+#endif
 #define FUSED_WARPS (FUSED_THREADS / 32)
 #ifndef FUSED_MAX_TILE
 #define FUSED_MAX_TILE MS_TILE_BYTES  // largest tile (and the default)
@@ -48,7 +57,7 @@
 #define FUSED_OFF_HIT (FUSED_OFF_TMASK + FUSED_MAX_NSEG * 2)
 #define FUSED_OFF_ROWS (FUSED_OFF_HIT + FUSED_HIT_WORDS * 4)
 #define FUSED_OFF_LUT ((FUSED_OFF_ROWS + (FUSED_ROWS_CAP + 2) * 2 + 15) / 16 * 16)
-#define FUSED_SMEM (FUSED_OFF_LUT + 512)
+#define FUSED_SMEM (FUSED_OFF_LUT + 512 + 256)  // + 256: the LUT starts at the next 256-byte boundary of the shared window
 static_assert(FUSED_OFF_CMASK % 16 == 0 && FUSED_OFF_TMASK % 16 == 0 && FUSED_OFF_HIT % 8 == 0 && FUSED_OFF_ROWS % 4 == 0,
               "shared memory layout");
 static_assert(FUSED_MAX_REGION + FUSED_PAD < 65536, "row starts are 16-bit");
@@ -118,8 +127,21 @@ __device__ __forceinline__ unsigned long long ld_relaxed_u64(const unsigned long
 __device__ __forceinline__ void st_relaxed_u64(unsigned long long* p, unsigned long long v) {
     asm volatile("st.relaxed.gpu.global.u64 [%0], %1;\n" ::"l"(p), "l"(v) : "memory");
 }
+// 0x80 in every byte of w that is a comma.  Exact for words of ASCII bytes; a byte >= 0x80 may spoil its neighbour's
+// flag, which is harmless: such a segment raises MS_LOAD_HIGH_BYTES and the caller discards this kernel's result.
+__device__ __forceinline__ uint32_t ms_comma_flags(uint32_t w) {
+#ifdef FUSED_EXACT_COMMAS
+    return ms_eq_flags(w, 0x2c2c2c2cu);
+#else
+    return ~((w ^ 0x2c2c2c2cu) + 0x7f7f7f7fu) & 0x80808080u;
+#endif
+}
 // barrier among the worker warps only (warp 0 is away looking back)
 __device__ __forceinline__ void ms_bar_workers(int n) { asm volatile("bar.sync 1, %0;\n" ::"r"(n) : "memory"); }
+// hand-off of the tile's aggregate: the first worker warp arrives on named barrier 2 after it wrote the aggregate to shared
+// memory, warp 0 waits on it (producer / consumer use of bar.arrive + bar.sync: the barrier orders the shared-memory writes)
+__device__ __forceinline__ void ms_bar_agg_arrive() { asm volatile("bar.arrive 2, 64;\n" ::: "memory"); }
+__device__ __forceinline__ void ms_bar_agg_wait() { asm volatile("bar.sync 2, 64;\n" ::: "memory"); }
 __device__ __forceinline__ uint32_t ld_acquire_u32(const uint32_t* p) {
     uint32_t v;
     asm volatile("ld.acquire.gpu.global.u32 %0, [%1];\n" : "=r"(v) : "l"(p) : "memory");
@@ -190,6 +212,11 @@ __device__ __forceinline__ uint32_t lds_u32(uint32_t a) {
     asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
     return v;
 }
+__device__ __forceinline__ uint2 lds_v2(uint32_t a) {
+    uint2 v;
+    asm volatile("ld.shared.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(a));
+    return v;
+}
 __device__ __forceinline__ uint4 lds_v4(uint32_t a) {
     uint4 v;
     asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
@@ -225,7 +252,7 @@ __device__ __forceinline__ bool ms_field_fast(uint32_t sreg, uint32_t sdm, uint3
     const uint32_t a0 = lds_u32(sw), a1 = lds_u32(sw + 4), a2 = lds_u32(sw + 8), a3 = lds_u32(sw + 12);
     const uint32_t t0w = __funnelshift_r(a0, a1, sh) ^ 0x30303030u, t1w = __funnelshift_r(a1, a2, sh) ^ 0x30303030u,
                    t2w = __funnelshift_r(a2, a3, sh) ^ 0x30303030u;
-    const uint4 in = lds_v4(slut + ((L & 15) << 4));  // the chars of this field
+    const uint4 in = lds_v4(slut | ((L & 15) << 4));  // the chars of this field
     // chars of the field that are not digits -> bit j of M (j = 0: 12 bytes before the delimiter)
     const uint32_t n0 = ((t0w + 0x76767676u) | t0w) & in.x & 0x80808080u, n1 = ((t1w + 0x76767676u) | t1w) & in.y & 0x80808080u,
                    n2 = ((t2w + 0x76767676u) | t2w) & in.z & 0x80808080u;
@@ -239,8 +266,8 @@ __device__ __forceinline__ bool ms_field_fast(uint32_t sreg, uint32_t sdm, uint3
     const int nfrac = hasdot ? 11 - dotj : 0;
     const int ndig = L - (int)neg - (int)hasdot;
     // the point taken out: chars before it from the view shifted by one byte
-    const uint4 keep = lds_v4(slut + ((hasdot ? nfrac & 15 : 12) << 4));
-    const uint4 dig = lds_v4(slut + ((ndig & 15) << 4));
+    const uint4 keep = lds_v4(slut | ((hasdot ? nfrac & 15 : 12) << 4));
+    const uint4 dig = lds_v4(slut | ((ndig & 15) << 4));
     const uint32_t h0 = t0w << 8, h1 = __funnelshift_l(t0w, t1w, 8), h2 = __funnelshift_l(t1w, t2w, 8);
     const uint32_t g0 = ((t0w & keep.x) | (h0 & ~keep.x)) & dig.x, g1 = ((t1w & keep.y) | (h1 & ~keep.y)) & dig.y,
                    g2 = ((t2w & keep.z) | (h2 & ~keep.z)) & dig.z;
@@ -248,7 +275,7 @@ __device__ __forceinline__ bool ms_field_fast(uint32_t sreg, uint32_t sdm, uint3
     const uint32_t N = (v0 * 10000u + ms_digits4_dp(g1)) * 10000u + ms_digits4_dp(g2);
     // 1 to 12 digits whose value fits 32 bits (leading zeros are free: "-0.000944047" has ten digits)
     const bool fast = (unsigned)(L - 1) <= 11u && (Md & (Md - 1u)) == 0u && ndig >= 1 && v0 <= 41u && (!hasdot || cd == '.');
-    const double2 pw = lds_d2(slut + 256 + ((nfrac & 15) << 4));
+    const double2 pw = lds_d2((slut | ((nfrac & 15) << 4)) + 256);
     const double an = (double)N;
     const double q0 = __dmul_rn(an, pw.y);
     const double r = __fma_rn(-q0, pw.x, an);
@@ -291,12 +318,14 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     __shared__ int s_lt_end, s_next_item, s_nchunks, s_nblank, s_blank_lo, s_blank_hi, s_quotes, s_stop;
     __shared__ uint32_t s_tile, s_flags, s_pre_nb, s_agg_nb, s_fatal;
     __shared__ unsigned long long s_agg_dist;
-    __shared__ int s_agg_ready;
     __shared__ unsigned long long s_pre_dist;
     __shared__ int s_q, s_commas;
     __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
     __shared__ __align__(8) unsigned long long s_stage_bar;
-    MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + FUSED_OFF_LUT);
+    // the field LUT on a 256-byte boundary of the shared window: an entry's address is then `base | index << 4`, one LOP3
+    const uint32_t lut_off = ((((uint32_t)__cvta_generic_to_shared(smem_raw) + FUSED_OFF_LUT + 255u) & ~255u) -
+                              (uint32_t)__cvta_generic_to_shared(smem_raw));
+    MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + lut_off);
     __shared__ uint32_t s_inv_groups;
     __shared__ int s_slow_n;
     __shared__ __align__(16) MsSecDesc s_desc;  // the descriptor of the section this tile starts in, fetched by warp 0
@@ -323,7 +352,6 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         s_quotes = 0;
         s_flags = 0;
         s_stop = 0;
-        s_agg_ready = 0;
         s_fatal = 0;
         s_slow_n = 0;
         s_desc_sec = -1;
@@ -484,13 +512,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             }
         }
 #endif
+        ms_bar_agg_wait();  // this tile's own share comes from the workers (shared memory)
         if (lane == 0) {
-            // this tile's own share comes from the workers (shared memory)
-            while (*(volatile int*)&s_agg_ready == 0) __nanosleep(20);
-            __threadfence_block();
             LbVal agg;
-            agg.nb = *(volatile uint32_t*)&s_agg_nb;
-            agg.dist = *(volatile unsigned long long*)&s_agg_dist;
+            agg.nb = s_agg_nb;
+            agg.dist = s_agg_dist;
             const LbVal incl = lb_combine(pre, agg);
             st_relaxed_u64(&lb[tile], lb_pack(LB_INCLUSIVE, incl));
             s_pre_nb = pre.nb;
@@ -554,9 +580,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
                 ctrl = ((x.x - 0x23232323u) | x.x) | ((x.y - 0x23232323u) | x.y) | ((x.z - 0x23232323u) | x.z) |
                        ((x.w - 0x23232323u) | x.w);
+#ifndef FUSED_LATE_COMMAS
                 // the commas of the segment, exactly; P1b adds the line-end bytes of the segments the test hit
                 cmask[v] = (uint16_t)ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu),
                                                ms_eq_flags(x.z, 0x2c2c2c2cu), ms_eq_flags(x.w, 0x2c2c2c2cu));
+#endif
             }
             const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
             if (lane == 0 && v < nseg_) hitmap[v >> 5] = hits;
@@ -594,7 +622,11 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 if ((x.x | x.y | x.z | x.w) & 0x80808080u) my_flags |= MS_LOAD_HIGH_BYTES;
                 const uint32_t term = ms_term16(lf, cr, reg[(v << 4) + 16] == '\n');
                 tmask[v] = (uint16_t)term;
+#ifdef FUSED_LATE_COMMAS
+                cmask[v] = (uint16_t)(lf | cr);  // a field also ends at a line end; P1c adds the commas
+#else
                 cmask[v] |= (uint16_t)(lf | cr);  // a field also ends at a line end: commas + line-end bytes = delimiters
+#endif
                 my_terms += __popc(term);
                 if (mine) {
                     const int p0 = v << 4;
@@ -692,12 +724,25 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
             s_agg_nb = agg.nb;
             s_agg_dist = agg.dist;
             s_fatal = fatal;
-            __threadfence_block();
-            *(volatile int*)&s_agg_ready = 1;
             if (s_quotes) atomicAdd((unsigned long long*)&res->n_quotes, (unsigned long long)s_quotes);
             const uint32_t f = s_flags | fatal | (nbw > 2 ? MS_LOAD_MANY_BLANKS : 0u);
             if (f) atomicOr(&res->flags, f);
         }
+        if (warp == 1) ms_bar_agg_arrive();
+#ifdef FUSED_LATE_COMMAS
+        // ---- P1c. the commas of every segment, exactly (delimiters = commas + the line-end bytes P1b left for the
+        // segments the quick test hit).  Nothing the other tiles wait for depends on them, so they are found AFTER the
+        // aggregate is out: the look-back of this tile and of its successors runs under this loop instead of after it.
+        for (int base = 0; base < nseg_; base += NW) {
+            const int v = base + wtid;
+            if (v < nseg_) {
+                const uint4 x = *reinterpret_cast<const uint4*>(reg + (v << 4));
+                uint32_t m = ms_mask16(ms_comma_flags(x.x), ms_comma_flags(x.y), ms_comma_flags(x.z), ms_comma_flags(x.w));
+                if ((hitmap[v >> 5] >> (v & 31)) & 1u) m |= cmask[v];
+                cmask[v] = (uint16_t)m;
+            }
+        }
+#endif
     }
     __syncthreads();
     fatal = s_fatal;
@@ -860,18 +905,33 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
         const uint32_t inv_groups = s_inv_groups;
         // one register holds the shared-window address of the staged bytes for the whole loop (a plain value would
         // be recomputed from the special registers at every use under this kernel's register budget)
+#ifdef FUSED_SMEM_SYM
+        // the shared-window address of the staged bytes as a link-time constant: ptxas folds it into the loads' offsets
+        uint32_t sreg;
+        asm("mov.u32 %0, smem_raw;" : "=r"(sreg));
+        sreg += FUSED_PAD;
+#else
         uint32_t sreg = (uint32_t)__cvta_generic_to_shared(reg);
 #ifndef FUSED_NO_PIN
         asm volatile("mov.u32 %0, %0;" : "+r"(sreg));
 #endif
-        const uint32_t sdm = sreg + (FUSED_OFF_CMASK - FUSED_PAD), slut = sreg + (FUSED_OFF_LUT - FUSED_PAD);
+#endif
+        const uint32_t sdm = sreg + (FUSED_OFF_CMASK - FUSED_PAD);
+        uint32_t slut = sreg - FUSED_PAD + lut_off;
+#ifdef FUSED_PIN_LUT
+        asm volatile("mov.u32 %0, %0;" : "+r"(slut));
+#endif
         double* const arena = args.arena;
         const uint32_t stride32 = (uint32_t)out_stride, out_idx0 = (uint32_t)(out_offset + out_row0);
+#ifdef FUSED_STATIC_ITEMS
+        for (int item = warp; item < items; item += FUSED_WARPS) {
+#else
         for (;;) {
             int item = 0;
             if (lane == 0) item = atomicAdd(&s_next_item, 1);
             item = __shfl_sync(0xffffffffu, item, 0);
             if (item >= items) break;
+#endif
             const int k = (int)(((uint32_t)item * inv_groups) >> 16), g = item - k * groups;  // chunk-major: wide chunks first
             const int r = (g << 5) + lane;
             if (r < nrows) {
@@ -881,6 +941,37 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                 if (c_lo > 0) {
                     // first byte of column c_lo = one past the c_lo-th comma of the row, if the row has it
                     const int row_end = row_start[Ld + r + 1];  // one past the row's terminator
+#ifdef FUSED_WALK64
+                    // four segments' delimiter masks (64 bytes of the row) per step
+                    const uint32_t sdm64 = (uint32_t)__cvta_generic_to_shared(cmask);
+                    int j = p >> 6;
+                    uint2 w = lds_v2(sdm64 + (j << 3));
+                    {
+                        const int b = p & 63;  // bits below the row's first byte belong to the row before
+                        const uint32_t below = b >= 32 ? 0xffffffffu : ((1u << b) - 1u);
+                        const uint32_t below_hi = b >= 32 ? ((1u << (b - 32)) - 1u) : 0u;
+                        w.x &= ~below;
+                        w.y &= ~below_hi;
+                    }
+                    int need = c_lo;
+                    int cnt = __popc(w.x) + __popc(w.y);
+                    while (cnt < need && (j << 6) < row_end) {
+                        need -= cnt;
+                        w = lds_v2(sdm64 + (++j << 3));
+                        cnt = __popc(w.x) + __popc(w.y);
+                    }
+                    if (cnt < need) {
+                        done = true;
+                    } else {
+                        const int clo = __popc(w.x);
+                        const bool up = need > clo;
+                        uint32_t m = up ? w.y : w.x;
+                        need -= up ? clo : 0;
+                        for (int i = 1; i < need; i++) m &= m - 1u;
+                        p = (j << 6) + (up ? 32 : 0) + __ffs(m);  // position after that delimiter
+                        if (p > row_end - 1) done = true;         // it belongs to a later row
+                    }
+#else
                     int seg = p >> 4;
                     uint32_t m = cmask[seg] & ~((1u << (p & 15)) - 1u);
                     int need = c_lo;
@@ -897,6 +988,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                         p = (seg << 4) + __ffs(m);  // position after that comma
                         if (p > row_end - 1) done = true;  // the comma belongs to a later row
                     }
+#endif
                 }
                 // element index into the arena, 32 bits (the entry point refuses larger arenas)
                 uint32_t oi = out_idx0 + (uint32_t)(c_lo - 2) * stride32 + (uint32_t)r;

@@ -202,6 +202,8 @@ class ViconLoader:
         self._pinned_head = torch.empty(_PEEK, dtype=torch.uint8, pin_memory=True)
         self._pinned_status = torch.empty(1, dtype=torch.int64, pin_memory=True)
         self._side_streams = None  # copy-in / copy-out streams of load_many, created on first use
+        self._pipe_stream = None  # load_device_many: the two streams its single-pass kernels are queued on in turn
+        self._work_stream = None  # high-priority stream offered to the caller of load_device_many
         # single-pass path: what the previous file looked like (sizes the next file's arena and tile), pinned
         # buffers on loan to results (data_model.HostLease), meta buffers, counters
         self._history = None
@@ -267,6 +269,86 @@ class ViconLoader:
             padded[:n].copy_(d_bytes[:n])
             d_bytes = padded
         return self._run(_Source(d_bytes, n, host), name, defer_check)
+
+    @property
+    def work_stream(self):
+        """A high-priority stream of this loader's device for the caller's own work on the trials that
+        `load_device_many` yields (Segmenter, window cuts): its small kernels then run beside the next trial's
+        loader kernel instead of behind it."""
+        if self._work_stream is None:
+            _, highest = self.torch.cuda.Stream.priority_range()
+            self._work_stream = self.torch.cuda.Stream(self.device, priority=highest)
+        return self._work_stream
+
+    def load_device_many(self, sources, names=None, depth: int = 2, defer_check: bool = True, stream=None):
+        """Trials whose CSV bytes are already in HBM, `depth` of them in flight (extension): yields one
+        ViconNexusData per source, in order.
+
+        sources: an iterable of CUDA uint8 tensors or (tensor, n) pairs, each readable to `padded_size(n)`.
+        The single-pass kernels of the next `depth` trials are queued on the loader's own pipeline streams (two,
+        taken in turn: consecutive trials are independent, so one kernel's last blocks and the next one's first
+        share the GPU) before a trial is handed to the caller, so the GPU parses trial i + 1 while the host finishes
+        the objects of trial i and the caller works on them.  stream: the stream the caller uses the results on
+        (default: the current one; `loader.work_stream` is a high-priority stream made for it).  What a trial's
+        data rows would have raised is raised when the trial is reached - by `data.check()` / `Segmenter(data)`
+        with defer_check, as for `load_device`.  A trial the single-pass kernel declines runs through the two-pass
+        path when it is reached; results are the same either way."""
+        import collections
+
+        torch = self.torch
+        if self._pipe_stream is None:
+            self._pipe_stream = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        it = iter(sources)
+        name_iter = iter(names) if names is not None else None
+        pending = collections.deque()
+        counter = [0]
+
+        def submit():
+            try:
+                item = next(it)
+            except StopIteration:
+                return False
+            d_bytes, n = item if isinstance(item, (tuple, list)) else (item, None)
+            n = int(d_bytes.numel() if n is None else n)
+            name = next(name_iter) if name_iter is not None else f"<device bytes {counter[0]}>"
+            counter[0] += 1
+            with self._lock, torch.cuda.device(self.device):
+                if d_bytes.numel() < _pad16(n):
+                    padded = torch.empty(_pad16(n), dtype=torch.uint8, device=self.device)
+                    padded[:n].copy_(d_bytes[:n])
+                    d_bytes = padded
+                src = _Source(d_bytes, n, None)
+                ticket = None
+                if FORCE_PATH != "two_pass" and n > 0:
+                    if self._fused_skip > 0 and FORCE_PATH != "fused":
+                        self._fused_skip -= 1
+                    else:
+                        # the bytes were written on the caller's stream: the pipeline stream reads them after that
+                        pipe = self._pipe_stream[counter[0] & 1]
+                        pipe.wait_stream(torch.cuda.current_stream(self.device))
+                        ticket = self._submit_fused(src, name, stream=pipe)
+            pending.append((src, name, ticket))
+            return True
+
+        while len(pending) < max(1, depth) and submit():
+            pass
+        while pending:
+            src, name, ticket = pending.popleft()
+            with self._lock, torch.cuda.device(self.device):
+                data = self._finish_fused(ticket) if ticket is not None else None
+                if data is not None:
+                    self.stats["fused"] += 1
+                    self._fused_backoff = 0
+                    # allocated on a pipeline stream, used (and let go) on the caller's
+                    cur = stream if stream is not None else torch.cuda.current_stream(self.device)
+                    for blk in data.blocks:
+                        if blk.tensor is not None:
+                            blk.tensor.record_stream(cur)
+                else:
+                    self.stats["two_pass"] += 1
+                    data = self._run_two_pass(src, name, defer_check)
+            submit()  # keep `depth` trials queued while the caller works on this one
+            yield data
 
     @staticmethod
     def padded_size(n: int) -> int:
@@ -405,6 +487,13 @@ class ViconLoader:
         """ms_load_fused: bytes -> both sections' blocks in one launch.  Returns None when the kernel (or the host's
         reading of the header text it sends back) says the file is not plain enough; the caller then runs the
         two-pass path, which handles - and words the errors of - everything."""
+        ticket = self._submit_fused(src, name)
+        return None if ticket is None else self._finish_fused(ticket)
+
+    def _submit_fused(self, src: _Source, name: str, stream=None):
+        """Queues ms_load_fused and the copy of its result word on `stream` (default: the loader's), builds the
+        objects of a file that looks like the previous one, and returns what `_finish_fused` needs - without
+        waiting for the GPU.  None: no size estimate (the caller runs the two-pass path)."""
         torch = self.torch
         mark = (lambda label: TIMELINE.append((label, time.perf_counter()))) if TIMELINE is not None else (lambda label: None)
         mark("enter")
@@ -413,10 +502,14 @@ class ViconLoader:
             return self._decline("no size estimate", back_off=False)
         arena_elems, cap1, cap2, tile, overhang = sizes
         self.last_plan = (tile, overhang)  # what the kernel was asked for (bench.py times the kernel with the same)
-        stream, sptr = self._stream_ptr()
+        if stream is None:
+            stream, sptr = self._stream_ptr()
+            on_stream = self._on_stream(stream)
+        else:
+            sptr, on_stream = ctypes.c_void_p(stream.cuda_stream), torch.cuda.stream(stream)
         meta = self._fmeta_acquire()
         d_meta, h_meta = meta
-        with self._on_stream(stream):
+        with on_stream:
             arena = torch.empty(arena_elems, dtype=torch.float64, device=self.device)
             ws_bytes = int(self.lib.ms_load_workspace_bytes(src.n, tile))
             ws = torch.empty(ws_bytes, dtype=torch.uint8, device=self.device)
@@ -441,6 +534,15 @@ class ViconLoader:
             except (TypeError, ValueError, KeyError):
                 ahead = None  # Builder.build would raise: on the ordinary path below, after the rows are known good
         mark("built ahead")
+        # arena / ws ride along: the kernel writes them until `copied`
+        return (src, name, arena, ws, meta, copied, ahead, prev_layouts, overhang)
+
+    def _finish_fused(self, ticket) -> Optional[ViconNexusData]:
+        """Waits for a submitted ms_load_fused, reads its result word and header text, and finishes the objects.
+        None: the file is not for the single-pass kernel (see _run_fused)."""
+        mark = (lambda label: TIMELINE.append((label, time.perf_counter()))) if TIMELINE is not None else (lambda label: None)
+        src, name, arena, ws, meta, copied, ahead, prev_layouts, overhang = ticket
+        d_meta, h_meta = meta
         copied.synchronize()
         mark("kernel done")
         host = h_meta.numpy()

@@ -222,3 +222,50 @@ def test_results_kept_across_a_batch_stay_valid(env):
 
     gc.collect()
     assert len(loader._host_pool) >= 2  # the buffers came back
+
+
+def test_stream_of_device_resident_trials(env):
+    """load_device_many: several trials in flight on the loader's pipeline streams, the caller's work on a stream of
+    its own - every trial's arrays bit-exact against the C oracle, transitions equal to a one-at-a-time load's, a trial
+    the single-pass kernel declines (a quoted field) answered by the two-pass path in its place, results kept across
+    the whole batch still valid."""
+    import torch
+
+    from muscle_synergies_b200.segment import Segmenter
+    from oracle import vicon_oracle_fast as vof
+    from tools.synth_vicon import synth_vicon
+
+    ms, loader_mod = env
+    loader_mod.FORCE_TILE = None
+    loader_mod.FORCE_PATH = None
+    blobs = [synth_vicon(seed=90 + i, seconds=4.0 + 0.5 * i, n_emg=16, n_markers=40, crlf=bool(i & 1)) for i in range(6)]
+    # trial 3: one quoted number in a data row - not for the single-pass kernel, same arrays from the two-pass path
+    text = blobs[3].tobytes()
+    cut = text.index(b",", text.index(b"\n", len(text) // 3) + 1) + 1  # start of the second field of a Devices row
+    end = text.index(b",", cut)
+    quoted = text[:cut] + b'"' + text[cut:end] + b'"' + text[end:]
+    blobs[3] = np.frombuffer(quoted, dtype=np.uint8)
+
+    def on_device(blob):
+        d = torch.empty(ms.ViconLoader.padded_size(blob.nbytes), dtype=torch.uint8, device="cuda")
+        d[: blob.nbytes].copy_(torch.from_numpy(np.ascontiguousarray(blob)))
+        return d, int(blob.nbytes)
+
+    sources = [on_device(b) for b in blobs]
+    loader = ms.ViconLoader()
+    work = loader.work_stream
+    kept, transitions = [], []
+    for data in loader.load_device_many(iter(sources), depth=3, stream=work):
+        with torch.cuda.stream(work):
+            seg = Segmenter(data)
+            transitions.append(list(seg.transitions))
+        kept.append(data)
+    torch.cuda.current_stream().wait_stream(work)
+    assert len(kept) == len(blobs)
+    assert loader.stats["fused"] >= 4 and loader.stats["two_pass"] >= 1, loader.stats
+    for i, (blob, data) in enumerate(zip(blobs, kept)):
+        want = vof.parse(blobs[i] if i != 3 else np.frombuffer(text, dtype=np.uint8))
+        got = section_arrays(data)
+        assert (bits(got[0]) == bits(want[0])).all() and (bits(got[1]) == bits(want[1])).all(), i
+        one = ms.ViconLoader().load_device(*sources[i])
+        assert list(Segmenter(one).transitions) == transitions[i]
