@@ -55,6 +55,7 @@ _header_cache = {}  # (header bytes, section, lines) -> parsed SectionLayout
 
 _READ_CHUNK = 32 << 20
 _READ_CHUNK_MIN = 2 << 20
+_READ_THREADS_MAX = int(os.environ.get("MS_B200_READ_THREADS", "16"))
 _read_pool = None
 
 # Which kernels load a file: None = the single-pass kernel (ms_load_fused) with the two-pass path
@@ -80,7 +81,9 @@ def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callabl
             cpus = len(os.sched_getaffinity(0))  # this process's share of the box (one rank per GPU binds a subset)
         except AttributeError:
             cpus = os.cpu_count() or 2
-        _read_pool = ThreadPoolExecutor(max_workers=max(2, min(8, cpus - 1)), thread_name_prefix="ms-read")
+        # preadv out of the page cache into pinned memory: 5 GB/s per thread, 34 GB/s with 8 and 45-53 GB/s with 15 threads
+        # on the 16-core share of a 1-GPU box (tools/read_probe.py); the PCIe link takes 55 GB/s
+        _read_pool = ThreadPoolExecutor(max_workers=max(2, min(_READ_THREADS_MAX, cpus - 1)), thread_name_prefix="ms-read")
     # two chunks per worker: a 100 MB trial keeps the whole pool busy (in 32 MB chunks it kept four threads busy)
     workers = _read_pool._max_workers
     chunk = min(_READ_CHUNK, max(_READ_CHUNK_MIN, -(-size // (2 * workers * _READ_CHUNK_MIN)) * _READ_CHUNK_MIN))

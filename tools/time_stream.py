@@ -42,6 +42,23 @@ def streamed(k, depth, hi=None):
         torch.cuda.current_stream().wait_stream(hi)
 
 
+def alloc_counts():
+    st = torch.cuda.memory_stats()
+    return st.get("num_device_alloc", 0), st.get("num_device_free", 0), st.get("num_alloc_retries", 0), torch.cuda.memory_reserved() >> 20
+
+
+def per_step(k, depth, hi):
+    """host wall time between yields: where a slow step is"""
+    import time
+    ts = [time.perf_counter()]
+    for data in loader.load_device_many(((d, n) for _ in range(k)), depth=depth, stream=hi):
+        with torch.cuda.stream(hi):
+            consume(data)
+        ts.append(time.perf_counter())
+    dt = sorted((b - a) * 1e3 for a, b in zip(ts, ts[1:]))
+    return dt[len(dt) // 2], dt[-1], dt[-3:]
+
+
 def timed(fn):
     torch.cuda.synchronize()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -62,6 +79,11 @@ for depth in (1, 2, 3):
     print(f"streamed depth {depth}     {timed(lambda: streamed(steps, depth)):.4f} ms/step")
     streamed(5, depth, hi)
     print(f"streamed depth {depth} hi  {timed(lambda: streamed(steps, depth, hi)):.4f} ms/step")
+for rep in range(4):
+    a0 = alloc_counts()
+    t = timed(lambda: streamed(steps, 2, hi))
+    print(f"rep {rep}: streamed depth 2 hi {t:.4f} ms/step   device allocs/frees/retries/reserved MB before {a0} after {alloc_counts()}")
+print("per-step wall (median, max, top3):", per_step(steps, 2, hi))
 # same results
 for data in loader.load_device_many(((d, n) for _ in range(3)), depth=2):
     seg, cuts = consume(data)
