@@ -282,6 +282,15 @@ int ms_nmf_mu_batched(const float* d_X, int32_t n, int32_t m, const int32_t* h_r
                       float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every, void* d_work,
                       int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
 
+/* The same launch without the host-to-device copy of the problem table and the wait behind it: ms_nmf_plan writes
+ * the table (32 bytes per problem) to host memory the caller owns and returns the largest rank (or MS_E_*); the caller
+ * keeps a device copy for as long as it runs that sweep (one launch per trial in pipeline.py) and passes it, with
+ * that rank, to ms_nmf_mu_batched_planned, which only queues the kernel. */
+int32_t ms_nmf_plan(int32_t n, int32_t m, const int32_t* h_ranks, const int32_t* h_x_index, int32_t n_problems, void* h_table);
+int ms_nmf_mu_batched_planned(const float* d_X, int32_t n, int32_t m, const void* d_table, int32_t n_problems, int32_t kmax,
+                              float* d_W, float* d_H, int32_t max_iter, float tol, int32_t check_every,
+                              int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream);
+
 /* Same contract for X of any length: X [n][m] and W [n][k] stream from HBM once per iteration
  * (algorithmic bytes per iteration and problem: 4 n m + 8 n k); W^T X and W^T W are reduced per
  * CTA and accumulated with atomics; the objective needs no extra pass over X.

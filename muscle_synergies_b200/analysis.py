@@ -15,7 +15,8 @@ import ctypes
 import functools
 from collections import OrderedDict
 from dataclasses import dataclass, field
-from typing import Mapping, Optional, Sequence, Union
+from collections.abc import Sequence
+from typing import Mapping, Optional, Union
 
 import numpy as np
 import pandas
@@ -28,8 +29,8 @@ from . import _native as nat
 class NMFBatchResult:
     ranks: np.ndarray          # (P,)
     seeds: np.ndarray          # (P,)
-    W: list                    # P arrays (n, k_p) float32
-    H: list                    # P arrays (k_p, m) float32
+    W: Sequence                # P arrays (n, k_p) float32 (views of one packed array, made on access)
+    H: Sequence                # P arrays (k_p, m) float32
     n_iter: np.ndarray         # (P,)
     err: np.ndarray            # (P,)  ||X - W H||_F
     vaf: np.ndarray            # (P, m + 1): overall, then per column
@@ -77,6 +78,34 @@ def _batch_draws(torch, n, m, ranks, seeds, dev):
     return hit
 
 
+_plan_cache = OrderedDict()  # (n, m, ranks, x_index, device) -> (device problem table, kmax, device ranks, x_index, element -> problem maps)
+
+
+def _batch_plan(torch, lib, n, m, ranks, xi, dev):
+    """The device-side description of a sweep (ms_nmf_plan's table, the ranks and matrix indices as int64 tensors), kept
+    for the sweeps a caller repeats: a pipeline runs the same one for every trial, and each copy from pageable memory
+    would wait for everything queued on the stream - the factorisation of the trial before."""
+    key = (n, m, ranks.tobytes(), xi.tobytes(), str(dev))
+    hit = _plan_cache.get(key)
+    if hit is None:
+        table = np.empty(len(ranks) * 32, dtype=np.uint8)
+        kmax = int(lib.ms_nmf_plan(n, m, ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)),
+                                   xi.ctypes.data_as(ctypes.POINTER(ctypes.c_int32)), len(ranks), table.ctypes.data))
+        nat.check(min(kmax, 0), "ms_nmf_plan")
+        r64 = ranks.astype(np.int64)
+        problem = np.arange(len(ranks), dtype=np.int64)
+        # which problem every element of the packed W / H belongs to (the per-problem scale of the random init is
+        # gathered through these; torch.repeat_interleave with device counts would wait for the device to size its output)
+        hit = (torch.from_numpy(table).to(dev), kmax, torch.from_numpy(r64).to(dev), torch.from_numpy(xi.astype(np.int64)).to(dev),
+               torch.from_numpy(np.repeat(problem, r64 * n)).to(dev), torch.from_numpy(np.repeat(problem, r64 * m)).to(dev))
+        _plan_cache[key] = hit
+        while len(_plan_cache) > 8:
+            _plan_cache.popitem(last=False)
+    else:
+        _plan_cache.move_to_end(key)
+    return hit
+
+
 _pinned_pool = {}  # nbytes -> pinned uint8 tensors not on loan (results of deferred runs travel through them)
 
 
@@ -96,10 +125,13 @@ class PendingNMF:
     for the copies and builds the NMFBatchResult.  Lets a caller queue the next trial's GPU work before it
     looks at this one's (pipeline.synergies_for_files)."""
 
-    def __init__(self, torch, stream, ranks, seeds, n, m, device_arrays, keep):
+    def __init__(self, torch, stream, ranks, seeds, n, m, device_arrays, keep, negative=None):
         self._ranks, self._seeds, self._n, self._m = ranks, seeds, n, m
         self._keep = keep  # inputs of the kernel: alive until the copies below have run
         self._bufs = []
+        self._negative = negative is not None  # a device flag "X has a negative entry" travels with the results
+        if negative is not None:
+            device_arrays = list(device_arrays) + [negative.to(torch.uint8).reshape(1)]
         for t in device_arrays:
             t = t.contiguous()
             buf = _pinned_take(torch, int(t.numel()) * t.element_size())
@@ -118,16 +150,38 @@ class PendingNMF:
                 out.append(buf.view(dtype).numpy().reshape(shape).copy())  # own memory: the pinned buffer goes back
                 _pinned_give(buf)
             self._bufs, self._keep = [], []
+            if self._negative and out.pop()[0]:
+                raise ValueError("Negative values in data passed to NMF (input X)")
             self._result = _assemble(self._ranks, self._seeds, self._n, self._m, *out)
         return self._result
 
 
+class _Factors(Sequence):
+    """The factors of a batch, problem after problem in one array: item p is a view, made when it is asked for (a
+    trial's batch has 1280 problems and its tables read 64 of them)."""
+
+    def __init__(self, packed: np.ndarray, offsets: np.ndarray, shapes):
+        self._packed, self._offsets, self._shapes = packed, offsets, shapes
+
+    def __len__(self):
+        return len(self._offsets) - 1
+
+    def __getitem__(self, p):
+        if isinstance(p, slice):
+            return [self[i] for i in range(*p.indices(len(self)))]
+        p = int(p)
+        if p < 0:
+            p += len(self)
+        if not 0 <= p < len(self):
+            raise IndexError(p)
+        return self._packed[self._offsets[p] : self._offsets[p + 1]].reshape(self._shapes(p))
+
+
 def _assemble(ranks, seeds, n, m, Wall, Hall, n_iter, err, vafs) -> NMFBatchResult:
-    P = len(ranks)
     w_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * n)])
     h_off = np.concatenate([[0], np.cumsum(ranks.astype(np.int64) * m)])
-    Ws = [Wall[w_off[p] : w_off[p + 1]].reshape(n, int(ranks[p])) for p in range(P)]
-    Hs = [Hall[h_off[p] : h_off[p + 1]].reshape(int(ranks[p]), m) for p in range(P)]
+    Ws = _Factors(Wall, w_off, lambda p: (n, int(ranks[p])))
+    Hs = _Factors(Hall, h_off, lambda p: (int(ranks[p]), m))
     return NMFBatchResult(ranks, seeds, Ws, Hs, n_iter, err, vafs)
 
 
@@ -162,7 +216,10 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
         shape = Xh.shape
     if len(shape) != 3 or 0 in shape:
         raise ValueError("X must be a non-empty (n, m) matrix or a (B, n, m) stack")
-    if bool((dX64 < 0).any()) if on_device else bool((Xh < 0).any()):
+    # a deferred run on device data does not wait for the answer here (it would wait for everything queued before it,
+    # the previous trial's factorisation included): the flag travels with the results and `.result()` raises
+    negative = (dX64 < 0).any() if on_device and defer else None
+    if negative is None and (bool((dX64 < 0).any()) if on_device else bool((Xh < 0).any())):
         raise ValueError("Negative values in data passed to NMF (input X)")
     B, n, m = shape
     ranks = np.ascontiguousarray(ranks, dtype=np.int32)
@@ -194,27 +251,39 @@ def nmf_mu_batched(X, ranks: Sequence[int], seeds: Sequence[int], max_iter: int 
                 means = dX64.mean(dim=(1, 2))
             else:
                 means = torch.from_numpy(np.array([Xh[b].mean() for b in range(B)])).to(dev)
-            d_ranks = torch.from_numpy(ranks.astype(np.int64)).to(dev)
-            avg = torch.sqrt(means[torch.from_numpy(xi.astype(np.int64)).to(dev)] / d_ranks)
-            dW = (unit_w * torch.repeat_interleave(avg, d_ranks * n)).to(torch.float32)
-            dH = (unit_h * torch.repeat_interleave(avg, d_ranks * m)).to(torch.float32)
-        work = torch.empty(max(P * 32, int(lib.ms_nmf_stream_workspace_bytes(m, P))), dtype=torch.uint8, device=dev)
+            _, _, d_ranks, d_xi, w_problem, h_problem = _batch_plan(torch, lib, n, m, ranks, xi, dev)
+            avg = torch.sqrt(means[d_xi] / d_ranks)
+            dW = (unit_w * avg[w_problem]).to(torch.float32)
+            dH = (unit_h * avg[h_problem]).to(torch.float32)
         d_iter = torch.empty(P, dtype=torch.int32, device=dev)
         d_err = torch.empty(P, dtype=torch.float32, device=dev)
         d_vaf = torch.empty((P, m + 1), dtype=torch.float32, device=dev)
-        h_ranks = ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
-        h_xi = xi.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
-        entry = lib.ms_nmf_mu_batched if resident else lib.ms_nmf_mu_stream
-        nat.check(
-            entry(
-                dX.data_ptr(), n, m, h_ranks, h_xi, P, dW.data_ptr(), dH.data_ptr(), int(max_iter), ctypes.c_float(tol),
-                int(check_every), work.data_ptr(), d_iter.data_ptr(), d_err.data_ptr(), d_vaf.data_ptr(),
-                ctypes.c_void_p(stream.cuda_stream),
-            ),
-            "ms_nmf_mu_batched" if resident else "ms_nmf_mu_stream",
-        )
+        if resident:
+            # the problem table lives on the device for as long as the sweep is repeated: the launch copies nothing
+            # and waits for nothing
+            work, kmax_plan = _batch_plan(torch, lib, n, m, ranks, xi, dev)[:2]
+            nat.check(
+                lib.ms_nmf_mu_batched_planned(
+                    dX.data_ptr(), n, m, work.data_ptr(), P, kmax_plan, dW.data_ptr(), dH.data_ptr(), int(max_iter),
+                    ctypes.c_float(tol), int(check_every), d_iter.data_ptr(), d_err.data_ptr(), d_vaf.data_ptr(),
+                    ctypes.c_void_p(stream.cuda_stream),
+                ),
+                "ms_nmf_mu_batched_planned",
+            )
+        else:
+            work = torch.empty(int(lib.ms_nmf_stream_workspace_bytes(m, P)), dtype=torch.uint8, device=dev)
+            h_ranks = ranks.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+            h_xi = xi.ctypes.data_as(ctypes.POINTER(ctypes.c_int32))
+            nat.check(
+                lib.ms_nmf_mu_stream(
+                    dX.data_ptr(), n, m, h_ranks, h_xi, P, dW.data_ptr(), dH.data_ptr(), int(max_iter), ctypes.c_float(tol),
+                    int(check_every), work.data_ptr(), d_iter.data_ptr(), d_err.data_ptr(), d_vaf.data_ptr(),
+                    ctypes.c_void_p(stream.cuda_stream),
+                ),
+                "ms_nmf_mu_stream",
+            )
         if defer:
-            return PendingNMF(torch, stream, ranks, seeds, n, m, [dW, dH, d_iter, d_err, d_vaf], [dX, work])
+            return PendingNMF(torch, stream, ranks, seeds, n, m, [dW, dH, d_iter, d_err, d_vaf], [dX, work], negative)
         Wall, Hall = dW.cpu().numpy(), dH.cpu().numpy()
         n_iter, err, vafs = d_iter.cpu().numpy(), d_err.cpu().numpy(), d_vaf.cpu().numpy()
     return _assemble(ranks, seeds, n, m, Wall, Hall, n_iter, err, vafs)

@@ -410,6 +410,50 @@ extern "C" int32_t ms_nmf_resident_max_rows(int32_t m, int32_t kmax) {
     return (int32_t)((budget - fixed) / per_row);
 }
 
+// The problem table of a batch (32 bytes per problem: rank, offsets of its W, H and X), written to HOST memory the
+// caller owns; returns the largest rank, or a negative MS_E_* code.  A caller that runs the same sweep again and again
+// (one launch per trial) copies the table to the device once and then uses ms_nmf_mu_batched_planned, which neither
+// copies nor waits.
+extern "C" int32_t ms_nmf_plan(int32_t n, int32_t m, const int32_t* h_ranks, const int32_t* h_x_index, int32_t n_problems,
+                               void* h_table) {
+    if (!h_ranks || !h_table || n < 1 || m < 1 || m > NMF_MAX_M || n_problems < 0) return MS_E_INVALID;
+    MsNmfProblem* h = (MsNmfProblem*)h_table;
+    long long wo = 0, ho = 0;
+    int kmax = 0;
+    for (int p = 0; p < n_problems; p++) {
+        const int k = h_ranks[p];
+        if (k < 1 || k > NMF_MAX_K) return MS_E_INVALID;
+        h[p].k = k;
+        h[p].w_off = wo;
+        h[p].h_off = ho;
+        h[p].x_off = h_x_index ? (long long)h_x_index[p] * n * m : 0;
+        if (h[p].x_off < 0) return MS_E_INVALID;
+        wo += (long long)n * k;
+        ho += (long long)k * m;
+        if (k > kmax) kmax = k;
+    }
+    return kmax;
+}
+
+// ms_nmf_mu_batched with the table of ms_nmf_plan already in device memory: one launch, nothing else.
+extern "C" int ms_nmf_mu_batched_planned(const float* d_X, int32_t n, int32_t m, const void* d_table, int32_t n_problems,
+                                         int32_t kmax, float* d_W, float* d_H, int32_t max_iter, float tol,
+                                         int32_t check_every, int32_t* d_n_iter, float* d_err, float* d_vaf, void* stream) {
+    if (!d_X || !d_table || !d_W || !d_H || !d_n_iter || !d_err || !d_vaf) return MS_E_INVALID;
+    if (n < 1 || m < 1 || m > NMF_MAX_M || kmax < 1 || kmax > NMF_MAX_K || n_problems < 0 || max_iter < 0 || check_every < 1)
+        return MS_E_INVALID;
+    if (n_problems == 0) return MS_OK;
+    if (n > ms_nmf_resident_max_rows(m, kmax)) return MS_E_INVALID;  // too long for the resident kernel: use ms_nmf_mu_stream
+    cudaStream_t st = (cudaStream_t)stream;
+    const size_t smem = ms_nmf_resident_smem(n, m, kmax);
+    MS_CUDA_CHECK(cudaFuncSetAttribute(ms_nmf_resident_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    ms_nmf_resident_kernel<<<n_problems, NMF_THREADS, smem, st>>>(d_X, n, m, (const MsNmfProblem*)d_table, d_W, d_H, max_iter,
+                                                                  tol, check_every, d_n_iter, d_err, d_vaf);
+    MS_COUNT_LAUNCH();
+    MS_CUDA_CHECK(cudaGetLastError());
+    return MS_OK;
+}
+
 // h_ranks[P]: rank of each problem; h_x_index[P] (may be NULL = all 0): which [n][m] matrix of d_X
 // problem p factorises.  d_W / d_H hold the initial factors packed problem after problem (W_p is
 // [n][k_p] row-major, H_p is [k_p][m]) and receive the results in place.

@@ -127,7 +127,8 @@ def time_normalize_windows(env, starts: Sequence[int], stops: Sequence[int], red
     torch = _torch()
     env = env if env.stride(1) == 1 else env.contiguous()
     n_ch = int(env.shape[0])
-    meta = torch.tensor([list(starts), list(stops)], dtype=torch.int64).to(env.device)
+    # through pinned memory, without waiting: a copy from pageable memory would wait for everything queued on the stream
+    meta = torch.tensor([list(starts), list(stops)], dtype=torch.int64, pin_memory=True).to(env.device, non_blocking=True)
     out = torch.empty((len(starts), reduce_to, n_ch), dtype=torch.float64, device=env.device)
     nat.check(
         nat.lib().ms_time_normalize_windows(env.data_ptr(), int(env.stride(0)), n_ch, meta[0].data_ptr(), meta[1].data_ptr(),

@@ -191,14 +191,27 @@ def synergies_for_files(paths: Sequence[str], loader: Optional[ViconLoader] = No
         except caught as exc:
             return path, exc
 
-    # one trial deep: the GPU work of trial i is queued before the host looks at the results of trial i - 1
+    # one trial deep: the GPU work of trial i is queued before the host looks at the results of trial i - 1.  The loader
+    # kernel of a trial runs on the loader's pipeline streams and its transition search on the loader's high-priority
+    # work stream - beside the factorisation of the trial before it, which fills the compute stream for milliseconds -
+    # so that the envelopes and the NMF launch of trial i are queued while trial i - 1 is still being factorised.
+    import torch
+
+    work = loader.work_stream
     prev = None
     for path, data in loader.load_files(paths, to_host=False):
         if isinstance(data, Exception):
             cur = (path, data)
         else:
             try:
-                cur = (path, trial_synergies(data, defer=True, **kwargs))
+                seg = kwargs.get("segmenter")
+                if seg is None:
+                    with torch.cuda.stream(work):
+                        for blk in data.blocks or ():
+                            if blk is not None and blk.tensor is not None:
+                                blk.tensor.record_stream(work)
+                        seg = Segmenter(data)
+                cur = (path, trial_synergies(data, defer=True, **dict(kwargs, segmenter=seg)))
             except caught as exc:
                 cur = (path, exc)
         if prev is not None:

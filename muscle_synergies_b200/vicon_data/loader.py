@@ -299,8 +299,7 @@ class ViconLoader:
         import collections
 
         torch = self.torch
-        if self._pipe_stream is None:
-            self._pipe_stream = (torch.cuda.Stream(self.device), torch.cuda.Stream(self.device))
+        pipes = self._pipes()
         it = iter(sources)
         name_iter = iter(names) if names is not None else None
         pending = collections.deque()
@@ -322,14 +321,11 @@ class ViconLoader:
                     d_bytes = padded
                 src = _Source(d_bytes, n, None)
                 ticket = None
-                if FORCE_PATH != "two_pass" and n > 0:
-                    if self._fused_skip > 0 and FORCE_PATH != "fused":
-                        self._fused_skip -= 1
-                    else:
-                        # the bytes were written on the caller's stream: the pipeline stream reads them after that
-                        pipe = self._pipe_stream[counter[0] & 1]
-                        pipe.wait_stream(torch.cuda.current_stream(self.device))
-                        ticket = self._submit_fused(src, name, stream=pipe)
+                if self._want_fused(n):
+                    # the bytes were written on the caller's stream: the pipeline stream reads them after that
+                    pipe = pipes[counter[0] & 1]
+                    pipe.wait_stream(torch.cuda.current_stream(self.device))
+                    ticket = self._submit_fused(src, name, stream=pipe)
             pending.append((src, name, ticket))
             return True
 
@@ -416,17 +412,29 @@ class ViconLoader:
                 src.windows.append((off2, host[_META_INFO + 16 : _META_INFO + 16 + cnt2].tobytes()))
         return summary, ws
 
+    def _want_fused(self, n: int) -> bool:
+        """Whether the single-pass kernel gets this file (call once per file: it counts down the back-off)."""
+        if FORCE_PATH == "two_pass" or n <= 0:
+            return False
+        if self._fused_skip > 0 and FORCE_PATH != "fused":
+            self._fused_skip -= 1  # the last files were not for the single-pass kernel: do not run both on every one
+            return False
+        return True
+
+    def _pipes(self):
+        """The two streams single-pass kernels of consecutive files are queued on in turn (batch entry points)."""
+        if self._pipe_stream is None:
+            self._pipe_stream = (self.torch.cuda.Stream(self.device), self.torch.cuda.Stream(self.device))
+        return self._pipe_stream
+
     def _run(self, src: _Source, name: str, defer_check: bool = False) -> ViconNexusData:
         with self._lock, self.torch.cuda.device(self.device):
-            if FORCE_PATH != "two_pass" and src.n > 0:
-                if self._fused_skip > 0 and FORCE_PATH != "fused":
-                    self._fused_skip -= 1  # the last files were not for the single-pass kernel: do not run both on every one
-                else:
-                    data = self._run_fused(src, name)
-                    if data is not None:
-                        self.stats["fused"] += 1
-                        self._fused_backoff = 0
-                        return data
+            if self._want_fused(src.n):
+                data = self._run_fused(src, name)
+                if data is not None:
+                    self.stats["fused"] += 1
+                    self._fused_backoff = 0
+                    return data
             self.stats["two_pass"] += 1
             return self._run_two_pass(src, name, defer_check)
 
@@ -764,18 +772,52 @@ class ViconLoader:
                 ev.record(s_copy)
             return (name, d_bytes, n, ev, pinned)
 
+        pipes = self._pipes()
+
+        def submit(staged):
+            """The single-pass kernel of a staged file, queued on a pipeline stream behind its host->device copy - not
+            behind whatever the caller has queued on the compute stream for the files before it."""
+            if staged is None or len(staged) == 2:
+                return None
+            name, d_bytes, n, ev, pinned = staged
+            src = _Source(d_bytes, n, pinned.numpy()[:n])
+            ticket = None
+            try:
+                with self._lock, torch.cuda.device(self.device):
+                    if self._want_fused(n):
+                        pipe = pipes[counter[0] & 1]
+                        pipe.wait_event(ev)
+                        d_bytes.record_stream(pipe)
+                        ticket = self._submit_fused(src, name, stream=pipe)
+            except Exception:  # noqa: BLE001 - the two-pass path below raises what there is to raise
+                ticket = None
+            return src, ticket
+
         i = 0
         nxt = stage()
+        nxt_sub = submit(nxt)
         while nxt is not None:
-            cur = nxt
-            nxt = stage()  # the next file's host->device copy is in flight while this one is parsed
+            cur, cur_sub = nxt, nxt_sub
+            nxt = stage()  # the next file's host->device copy and its kernel are in flight while this one is finished
+            nxt_sub = submit(nxt)
             try:
                 if len(cur) == 2:
                     raise cur[1]
                 name, d_bytes, n, ev, pinned = cur
-                s_comp.wait_event(ev)
-                d_bytes.record_stream(s_comp)
-                data = self._run(_Source(d_bytes, n, pinned.numpy()[:n]), name)
+                src, ticket = cur_sub
+                with self._lock, torch.cuda.device(self.device):
+                    data = self._finish_fused(ticket) if ticket is not None else None
+                    if data is not None:
+                        self.stats["fused"] += 1
+                        self._fused_backoff = 0
+                        for blk in data.blocks:  # allocated on a pipeline stream, used on the compute stream
+                            if blk.tensor is not None:
+                                blk.tensor.record_stream(s_comp)
+                    else:
+                        s_comp.wait_event(ev)
+                        d_bytes.record_stream(s_comp)
+                        self.stats["two_pass"] += 1
+                        data = self._run_two_pass(src, name)
             except Exception as exc:  # noqa: BLE001
                 if not return_exceptions:
                     raise
