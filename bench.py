@@ -601,12 +601,29 @@ def run_ours(args):
                 blk.host()
             torch.cuda.synchronize()
 
+        # what the HOST delivers with every rank reading at once: the same files copied out of the page cache into a
+        # pinned buffer by the loader's reader pool, nothing else running (the ceiling of this leg and of configs[4])
+        def read_only():
+            buf = torch.empty(loader.padded_size(max(os.path.getsize(p) for p in mine)), dtype=torch.uint8, pin_memory=True)
+            for p in mine:
+                loader_mod.read_file_into(p, buf.numpy(), os.path.getsize(p))
+
+        read_only()
+        barrier()
+        t = time.perf_counter()
+        read_only()
+        read_wall = max_over_ranks(time.perf_counter() - t)
+        read_ceiling = sum(sizes) / read_wall / 1e9
+
         run_files()
         barrier()
         t = time.perf_counter()
         run_files()
         wall = max_over_ranks(time.perf_counter() - t)
         files_leg = {"value": sum(sizes) / wall / 1e9, "unit": UNIT, "files": n_files, "files_per_rank": len(mine),
+                     "host_read_ceiling": read_ceiling, "frac_of_host_read_ceiling": sum(sizes) / wall / 1e9 / read_ceiling,
+                     "host_read_note": "page cache -> pinned memory by the reader pools of all ranks at once, no GPU work",
+                     "reader_threads_per_rank": loader_mod._read_pool._max_workers if loader_mod._read_pool is not None else None,
                      "mb_per_file": sizes[0] / 1e6, "ms_per_file_per_rank": wall / max(1, len(mine)) * 1e3,
                      "where": "tmpfs" if base else "temp directory", "bytes_this_rank": my_bytes,
                      "api": "ViconLoader.load_files (reader thread -> pinned ring -> H2D / parse / D2H) -> host arrays; "
@@ -630,6 +647,7 @@ def run_ours(args):
                                     "k=1..8 x 20 restarts x 200 it; best-of-restarts VAF tables gathered on the host",
                         "trials": n_files, "cycles": n_cycles, "cycles_per_s": n_cycles / wall, "ms_per_trial_per_rank": wall / per_rank * 1e3,
                         "table_rows": len(table), "failed_files": len(table) - len(ok_rows),
+                        "csv_gbs": sum(sizes) / wall / 1e9, "frac_of_host_read_ceiling": sum(sizes) / wall / 1e9 / read_ceiling,
                         "timing": "wall clock, max over ranks, files in tmpfs; second pass over the file list (allocator and pinned pools warm)"}
         barrier()
         if rank == 0:

@@ -65,3 +65,28 @@ def test_product_does_not_import_oracle():
                 text = open(os.path.join(base, f), errors="ignore").read()
                 assert "import oracle" not in text and "from oracle" not in text, f
                 assert "vicon_oracle" not in text and "libvicon_oracle" not in text, f
+
+
+def test_nmf_plan_is_host_only_and_lays_the_batch_out():
+    """ms_nmf_plan (pure host code): the problem table a repeated sweep keeps on the device - rank, then the offsets
+    of each problem's W, H and X in the packed arrays (32 bytes per problem)."""
+    import numpy as np
+
+    from muscle_synergies_b200 import _native
+
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    lib.ms_nmf_plan.restype = ctypes.c_int32
+    i32p = ctypes.POINTER(ctypes.c_int32)
+    ranks = np.array([1, 3, 8, 2], dtype=np.int32)
+    xi = np.array([0, 0, 1, 2], dtype=np.int32)
+    n, m = 200, 16
+    table = np.zeros(len(ranks) * 4, dtype=np.int64)
+    kmax = lib.ms_nmf_plan(n, m, ranks.ctypes.data_as(i32p), xi.ctypes.data_as(i32p), len(ranks), ctypes.c_void_p(table.ctypes.data))
+    assert kmax == 8
+    rows = table.reshape(len(ranks), 4)
+    assert (rows[:, 0] & 0xFFFFFFFF).tolist() == ranks.tolist()
+    assert rows[:, 1].tolist() == [0, 200, 800, 2400]          # W offsets: n * sum of the ranks before
+    assert rows[:, 2].tolist() == [0, 16, 64, 192]             # H offsets: m * sum of the ranks before
+    assert rows[:, 3].tolist() == [0, 0, n * m, 2 * n * m]     # X offsets: matrix index * n * m
+    bad = np.array([0], dtype=np.int32)
+    assert lib.ms_nmf_plan(n, m, bad.ctypes.data_as(i32p), None, 1, ctypes.c_void_p(table.ctypes.data)) < 0
