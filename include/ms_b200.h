@@ -305,6 +305,10 @@ int ms_nmf_mu_stream(const float* d_X, int64_t n, int32_t m, const int32_t* h_ra
  * memory as one 2-D copy on the DMA engine; asynchronous when h_dst is page-locked. */
 int ms_copy_rows_to_host(void* h_dst, int64_t dst_pitch_bytes, const void* d_src, int64_t src_pitch_bytes,
                          int64_t width_bytes, int64_t rows, void* stream);
+/* Host to host copy with non-temporal stores (no read of the destination's cache lines): what the file readers use to
+ * move a mapped file out of the page cache into the pinned buffer the DMA engine reads (load_csv.py:29 opens the file;
+ * everything after that is this library's). */
+int ms_host_copy_stream(void* h_dst, const void* h_src, int64_t n_bytes);
 /* Text of the last CUDA failure reported (MS_E_CUDA) to the calling thread. */
 const char* ms_last_cuda_error(void);
 const char* ms_version(void);

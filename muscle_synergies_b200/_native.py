@@ -132,6 +132,7 @@ def _declare(L):
         "ms_nmf_resident_max_rows": (i32, [i32, i32]),
         "ms_nmf_mu_batched": (ctypes.c_int, [vp, i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp, vp, i32,
                                              ctypes.c_float, i32, vp, vp, vp, vp, vp]),
+        "ms_host_copy_stream": (ctypes.c_int, [vp, vp, i64]),
         "ms_nmf_plan": (i32, [i32, i32, ctypes.POINTER(i32), ctypes.POINTER(i32), i32, vp]),
         "ms_nmf_mu_batched_planned": (ctypes.c_int, [vp, i32, i32, vp, i32, i32, vp, vp, i32, ctypes.c_float, i32, vp, vp, vp, vp]),
         "ms_nmf_stream_workspace_bytes": (i64, [i32, i32]),

@@ -90,3 +90,24 @@ def test_nmf_plan_is_host_only_and_lays_the_batch_out():
     assert rows[:, 3].tolist() == [0, 0, n * m, 2 * n * m]     # X offsets: matrix index * n * m
     bad = np.array([0], dtype=np.int32)
     assert lib.ms_nmf_plan(n, m, bad.ctypes.data_as(i32p), None, 1, ctypes.c_void_p(table.ctypes.data)) < 0
+
+
+def test_host_copy_stream_copies_exactly():
+    """ms_host_copy_stream (pure host code, non-temporal stores): every size and alignment, nothing outside the range."""
+    import numpy as np
+
+    from muscle_synergies_b200 import _native
+
+    lib = ctypes.CDLL(_native.LIB_PATH)
+    lib.ms_host_copy_stream.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int64]
+    rng = np.random.default_rng(0)
+    for n in (0, 1, 15, 63, 64, 65, 127, 1000, 4096, (1 << 20) + 7):
+        for src_off in (0, 3):
+            for dst_off in (0, 5, 17, 48):
+                src = rng.integers(0, 255, n + src_off + 64, dtype=np.uint8)
+                dst = np.zeros(n + dst_off + 64, dtype=np.uint8)
+                assert lib.ms_host_copy_stream(dst.ctypes.data + dst_off, src.ctypes.data + src_off, n) == 0
+                assert (dst[dst_off : dst_off + n] == src[src_off : src_off + n]).all()
+                assert dst[:dst_off].sum() == 0 and dst[dst_off + n :].sum() == 0
+    assert lib.ms_host_copy_stream(None, None, 0) == 0
+    assert lib.ms_host_copy_stream(None, None, 8) < 0
