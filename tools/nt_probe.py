@@ -11,6 +11,11 @@ import numpy as np
 import torch
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+if not os.path.exists(os.path.join(HERE, "libcopy_nt_probe.so")):
+    import subprocess
+
+    subprocess.check_call(["gcc", "-O2", "-mavx2", "-shared", "-fPIC", os.path.join(HERE, "copy_nt_probe.c"), "-o",
+                           os.path.join(HERE, "libcopy_nt_probe.so")])
 nt = ctypes.CDLL(os.path.join(HERE, "libcopy_nt_probe.so"))
 nt.copy_nt.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_size_t]
 size = 105_000_000

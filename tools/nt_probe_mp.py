@@ -12,6 +12,11 @@ from concurrent.futures import ThreadPoolExecutor
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
+if not os.path.exists(os.path.join(HERE, "libcopy_nt_probe.so")):
+    import subprocess
+
+    subprocess.check_call(["gcc", "-O2", "-mavx2", "-shared", "-fPIC", os.path.join(HERE, "copy_nt_probe.c"), "-o",
+                           os.path.join(HERE, "libcopy_nt_probe.so")])
 size = 105_000_000
 FILES = 6
 
