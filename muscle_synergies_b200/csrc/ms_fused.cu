@@ -34,7 +34,9 @@
 //                      widths from a per-section table, instead of taking equal static shares of the tile's (row group,
 //                      column) pairs; A/B: the static shares are 4 % faster (T10 0.580 -> 0.555 ms, T127 0.160 -> 0.154 ms)
 #ifndef FUSED_AB_BASE
+#ifndef FUSED_EARLY_COMMAS
 #define FUSED_LATE_COMMAS
+#endif
 #define FUSED_WALK64
 #define FUSED_PIN_LUT
 #endif
@@ -320,18 +322,21 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
     uint32_t* const hitmap = reinterpret_cast<uint32_t*>(smem_raw + FUSED_OFF_HIT);   // segments with a byte < 0x23 or >= 0x80
     uint16_t* const row_start = reinterpret_cast<uint16_t*>(smem_raw + FUSED_OFF_ROWS);  // [L]: first byte of local row L
     __shared__ int s_warp_terms[FUSED_WARPS];
-    __shared__ int s_lt_end, s_next_item, s_nchunks, s_nblank, s_blank_lo, s_blank_hi, s_quotes, s_stop;
+    __shared__ int s_lt_end, s_nblank, s_blank_lo, s_blank_hi, s_quotes, s_stop;
+#ifdef FUSED_DYNAMIC_ITEMS
+    __shared__ int s_next_item, s_nchunks;
+    __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
+    __shared__ uint32_t s_inv_groups;
+#endif
     __shared__ uint32_t s_tile, s_flags, s_pre_nb, s_agg_nb, s_fatal;
     __shared__ unsigned long long s_agg_dist;
     __shared__ unsigned long long s_pre_dist;
     __shared__ int s_q, s_commas;
-    __shared__ int s_chunk_col[PARSE_MAX_CHUNKS + 1];
     __shared__ __align__(8) unsigned long long s_stage_bar;
     // the field LUT on a 256-byte boundary of the shared window: an entry's address is then `base | index << 4`, one LOP3
     const uint32_t lut_off = ((((uint32_t)__cvta_generic_to_shared(smem_raw) + FUSED_OFF_LUT + 255u) & ~255u) -
                               (uint32_t)__cvta_generic_to_shared(smem_raw));
     MsFieldLut* const lut_p = reinterpret_cast<MsFieldLut*>(smem_raw + lut_off);
-    __shared__ uint32_t s_inv_groups;
     __shared__ int s_slow_n;
     __shared__ __align__(16) MsSecDesc s_desc;  // the descriptor of the section this tile starts in, fetched by warp 0
     __shared__ int s_desc_sec;                  // which section s_desc describes; -1: none (not published at the time)
@@ -393,11 +398,9 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                          : "memory");
         }
     }
-    for (int i = tid; i < n_chunks_smem; i += FUSED_THREADS) {
-        if (i >= lo_chunk && i < hi_chunk) {
-            if (lo_chunk == 0 && hi_chunk == n_chunks_smem) break;  // the usual tile: nothing by hand
-            continue;
-        }
+    const bool by_hand = !(lo_chunk == 0 && hi_chunk == n_chunks_smem);  // the usual tile: nothing by hand
+    for (int i = tid; by_hand && i < n_chunks_smem; i += FUSED_THREADS) {
+        if (i >= lo_chunk && i < hi_chunk) continue;
         const long long off = off0 + (long long)i * 16;
         uint4 v = make_uint4(0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au, 0x0a0a0a0au);
         if (off >= 0 && off < n) {
@@ -587,8 +590,7 @@ __global__ void __launch_bounds__(FUSED_THREADS, FUSED_MIN_CTAS)
                        ((x.w - 0x23232323u) | x.w);
 #ifndef FUSED_LATE_COMMAS
                 // the commas of the segment, exactly; P1b adds the line-end bytes of the segments the test hit
-                cmask[v] = (uint16_t)ms_mask16(ms_eq_flags(x.x, 0x2c2c2c2cu), ms_eq_flags(x.y, 0x2c2c2c2cu),
-                                               ms_eq_flags(x.z, 0x2c2c2c2cu), ms_eq_flags(x.w, 0x2c2c2c2cu));
+                cmask[v] = (uint16_t)ms_mask16(ms_comma_flags(x.x), ms_comma_flags(x.y), ms_comma_flags(x.z), ms_comma_flags(x.w));
 #endif
             }
             const uint32_t hits = __ballot_sync(0xffffffffu, in && (ctrl & 0x80808080u));
