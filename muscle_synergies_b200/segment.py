@@ -239,6 +239,19 @@ _PLAN_WORDS = 32 + 32 + 33  # starts, stops, offsets of the 32 phase windows of 
 VERIFY_DEVICE_PLAN = os.environ.get("MS_B200_VERIFY_PLAN") == "1"
 
 
+class PendingSegmenter:
+    """A Segmenter whose GPU work is queued (`Segmenter.begin`): `finish()` waits for it and completes the object."""
+
+    def __init__(self, seg: "Segmenter", begun):
+        self._seg, self._begun = seg, begun
+
+    def finish(self) -> "Segmenter":
+        if self._begun is not None:
+            begun, self._begun = self._begun, None
+            self._seg._complete(*begun)
+        return self._seg
+
+
 class Segmenter:
     """Segments a trial into trechos, cycles and phases from the two force plates."""
 
@@ -246,6 +259,18 @@ class Segmenter:
         """`cut_phases_of` (extension): devices of `data` whose 32 phase windows are gathered on the GPU
         in the same submission as the transition search (no host round trip in between); read them
         with `phase_cuts(device)`.  A trial loaded with `defer_check=True` is checked here."""
+        self._complete(*self._begin(data, min_phase_size, num_segments, cut_phases_of))
+
+    @classmethod
+    def begin(cls, data: ViconNexusData, min_phase_size: int = 10, num_segments: int = 40, cut_phases_of=()) -> "PendingSegmenter":
+        """Queues the transition search and the window gathers of `Segmenter(data, ...)` on the current stream and
+        returns at once (extension): `.finish()` waits for them and gives the Segmenter - what the constructor would
+        have raised is raised there.  A caller that works through a stream of trials starts trial i + 1 before it
+        finishes trial i, and never stands waiting for a search."""
+        seg = cls.__new__(cls)
+        return PendingSegmenter(seg, seg._begin(data, min_phase_size, num_segments, cut_phases_of))
+
+    def _begin(self, data: ViconNexusData, min_phase_size: int, num_segments: int, cut_phases_of):
         left_fp, right_fp = data.forcepl  # exactly two plates, like reactions()
         self._data = data
         precut = list(cut_phases_of)
@@ -256,6 +281,11 @@ class Segmenter:
                                    extra_words=_PLAN_WORDS * len(precut),
                                    plans=[self._plan_args(dev, left_fp) for dev in in_launch])
         queued = [self._queue_phase_cuts(search, dev, i, left_fp, planned=i < len(in_launch)) for i, dev in enumerate(precut)]
+        return search, queued
+
+    def _complete(self, search: "_TransitionSearch", queued):
+        data = self._data
+        left_fp = data.forcepl[0]
         try:
             self.transitions, self._loaded, extra = search.finish()
         finally:

@@ -257,7 +257,8 @@ def test_stream_of_device_resident_trials(env):
     kept, transitions = [], []
     for data in loader.load_device_many(iter(sources), depth=3, stream=work):
         with torch.cuda.stream(work):
-            seg = Segmenter(data)
+            # odd trials through the deferred constructor (search queued, finished a moment later)
+            seg = Segmenter.begin(data).finish() if len(kept) & 1 else Segmenter(data)
             transitions.append(list(seg.transitions))
         kept.append(data)
     torch.cuda.current_stream().wait_stream(work)
