@@ -102,7 +102,7 @@ def read_file_into(name, view: np.ndarray, size: int, on_chunk: Optional[Callabl
         # with non-temporal stores - a third less DRAM traffic per byte, which is what several ranks reading at once are
         # bound by (4 processes x 3 threads: 44 -> 58 GB/s).  Many threads in one process: preadv, which does not
         # contend for the address space's lock on page faults (15 threads: 44 GB/s against 39.5 mapped).
-        if _READ_MODE == "mmap" or (_READ_MODE == "auto" and workers <= 8 and size >= (1 << 20)):
+        if size > 0 and (_READ_MODE == "mmap" or (_READ_MODE == "auto" and workers <= 8 and size >= (1 << 20))):
             if os.fstat(fd).st_size < size:
                 raise IOError(f"short read on {name}: the file has fewer than {size} bytes")
             import mmap

@@ -3,12 +3,18 @@ import numpy as np
 import pytest
 
 
-def test_read_file_into_matches_plain_read(tmp_path):
+@pytest.mark.parametrize("mode", ["preadv", "mmap"])
+def test_read_file_into_matches_plain_read(tmp_path, mode):
+    """Both ways a file reaches the staging buffer: preadv, and a mapping of the file copied with non-temporal stores."""
+    import __graft_entry__ as g
+
+    g.build()
     from muscle_synergies_b200.vicon_data import loader
 
     rng = np.random.default_rng(0)
-    old = loader._READ_CHUNK
+    old, old_mode = loader._READ_CHUNK, loader._READ_MODE
     loader._READ_CHUNK = 1 << 16  # many chunks on a small file
+    loader._READ_MODE = mode
     try:
         for size in (0, 1, 65535, 65536, 65537, 1_000_003):
             data = rng.integers(0, 256, size, dtype=np.uint8)
@@ -24,7 +30,7 @@ def test_read_file_into_matches_plain_read(tmp_path):
             if seen:
                 assert seen[0][0] == 0 and seen[-1][0] + seen[-1][1] == size
     finally:
-        loader._READ_CHUNK = old
+        loader._READ_CHUNK, loader._READ_MODE = old, old_mode
     with pytest.raises(FileNotFoundError):
         loader.read_file_into(str(tmp_path / "missing"), np.empty(8, dtype=np.uint8), 8)
 
@@ -59,3 +65,34 @@ def test_batch_index_conversions_equal_the_scalar_ones():
     for bad in ([(0, 0)], [(51, 0)], [(1, 20)], [(1, -1)]):
         with pytest.raises(IndexError):
             emg.to_index_many(bad)
+
+
+def test_batch_factor_views_are_made_on_access():
+    """analysis._assemble: the factors of a batch stay one packed array; item p is a view of the right shape."""
+    from muscle_synergies_b200.analysis import _assemble
+
+    ranks = np.array([1, 3, 2], dtype=np.int32)
+    seeds = np.array([7, 8, 9], dtype=np.int64)
+    n, m = 5, 4
+    Wall = np.arange(n * ranks.sum(), dtype=np.float32)
+    Hall = np.arange(m * ranks.sum(), dtype=np.float32) + 100
+    res = _assemble(ranks, seeds, n, m, Wall, Hall, np.zeros(3, np.int32), np.zeros(3, np.float32), np.zeros((3, m + 1), np.float32))
+    assert len(res.W) == 3 and len(res.H) == 3
+    assert res.W[1].shape == (n, 3) and res.H[1].shape == (3, m)
+    assert res.W[1][0, 0] == n * 1 and res.H[2][0, 0] == 100 + m * 4
+    assert res.W[-1].shape == (n, 2) and [w.shape for w in res.W[0:2]] == [(n, 1), (n, 3)]
+    assert np.shares_memory(res.W[2], Wall)
+    import pytest
+
+    with pytest.raises(IndexError):
+        res.W[3]
+
+
+def test_stream_entry_points_exist_without_a_gpu():
+    """The batch extensions are part of the package's surface (they need a GPU to run, not to import)."""
+    from muscle_synergies_b200.segment import PendingSegmenter, Segmenter
+    from muscle_synergies_b200.vicon_data import ViconLoader
+
+    assert callable(getattr(ViconLoader, "load_device_many")) and callable(getattr(ViconLoader, "load_many"))
+    assert isinstance(getattr(ViconLoader, "work_stream"), property)
+    assert callable(Segmenter.begin) and callable(PendingSegmenter.finish)
