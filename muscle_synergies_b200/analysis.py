@@ -13,6 +13,7 @@ nndsvd inits, regularisation ...) is forwarded to scikit-learn, exactly as the r
 """
 import ctypes
 import functools
+import threading
 from collections import OrderedDict
 from dataclasses import dataclass, field
 from collections.abc import Sequence
@@ -61,6 +62,11 @@ _draw_cache = OrderedDict()  # (n, m, ranks, seeds, device) -> unit draws of the
 
 
 def _batch_draws(torch, n, m, ranks, seeds, dev):
+    with _cache_lock:
+        return _batch_draws_locked(torch, n, m, ranks, seeds, dev)
+
+
+def _batch_draws_locked(torch, n, m, ranks, seeds, dev):
     key = (n, m, ranks.tobytes(), seeds.tobytes(), str(dev))
     hit = _draw_cache.get(key)
     if hit is None:
@@ -81,7 +87,15 @@ def _batch_draws(torch, n, m, ranks, seeds, dev):
 _plan_cache = OrderedDict()  # (n, m, ranks, x_index, device) -> (device problem table, kmax, device ranks, x_index, element -> problem maps)
 
 
+_cache_lock = threading.Lock()  # the two caches below are process-wide; batches may be launched from several threads
+
+
 def _batch_plan(torch, lib, n, m, ranks, xi, dev):
+    with _cache_lock:
+        return _batch_plan_locked(torch, lib, n, m, ranks, xi, dev)
+
+
+def _batch_plan_locked(torch, lib, n, m, ranks, xi, dev):
     """The device-side description of a sweep (ms_nmf_plan's table, the ranks and matrix indices as int64 tensors), kept
     for the sweeps a caller repeats: a pipeline runs the same one for every trial, and each copy from pageable memory
     would wait for everything queued on the stream - the factorisation of the trial before."""
