@@ -96,3 +96,29 @@ def test_stream_entry_points_exist_without_a_gpu():
     assert callable(getattr(ViconLoader, "load_device_many")) and callable(getattr(ViconLoader, "load_many"))
     assert isinstance(getattr(ViconLoader, "work_stream"), property)
     assert callable(Segmenter.begin) and callable(PendingSegmenter.finish)
+
+
+def test_reader_pool_is_sized_to_the_ranks_share_of_the_box(tmp_path, monkeypatch):
+    """One process per GPU (torchrun sets LOCAL_WORLD_SIZE): each rank's reader pool takes its share of the cores, so
+    that eight ranks do not run eight full-size pools on one box; few threads -> mapped file + streamed copy."""
+    import os
+
+    from muscle_synergies_b200.vicon_data import loader
+
+    cpus = len(os.sched_getaffinity(0))
+    data = np.arange(3 << 20, dtype=np.uint8)
+    path = tmp_path / "f.bin"
+    data.tofile(path)
+    old_pool = loader._read_pool
+    try:
+        for world, want in ((1, max(2, min(loader._READ_THREADS_MAX, cpus - 1))),
+                            (8, max(2, min(loader._READ_THREADS_MAX, max(1, cpus // 8) - 1)))):
+            monkeypatch.setenv("LOCAL_WORLD_SIZE", str(world))
+            loader._read_pool = None
+            buf = np.zeros(data.size, dtype=np.uint8)
+            loader.read_file_into(str(path), buf, data.size)
+            assert loader._read_pool._max_workers == want
+            assert np.array_equal(buf, data)
+            loader._read_pool.shutdown()
+    finally:
+        loader._read_pool = old_pool
